@@ -1,0 +1,185 @@
+"""oracle/make_golden.py -- TEST INFRASTRUCTURE ONLY.
+
+Generates the committed golden vectors under tests/golden/ by importing the UNMODIFIED reference from
+/root/reference (read-only) in the build container and running its own modules on seeded inputs:
+
+  * models/wavelet.py:6-50          WaveletTransform(scale=2) dec / rec      -> dwt_kat.npz
+  * models/wavelet_weights_c2.pkl   rec4 weights                             -> dwt_kat.npz['rec4']
+  * models/unet.py:196-395          DiffusionUNet (small + full config)      -> unet_small.npz, unet_full.npz
+  * utils/sampling.py:10-13         compute_alpha                            -> ddim_small.npz['alphas']
+  * models/ddm_wavelet.py:437-506   generalized_steps_overlapping            -> ddim_small.npz
+  * models/ddm_wavelet.py:87-105    get_beta_schedule                        -> ddim_small.npz['betas']
+  * models/restoration.py:63-168    the DWT -> sample -> x0_preds[-5] -> IWT -> clamp sandwich (config #1,
+                                    with HFRM bypassed: x_other = HF bands of the DWT of the synthetic
+                                    gt)                                      -> sandwich_full.npz
+
+It also checks, while it runs, that the oracle restatements (oracle/unet_oracle.py, oracle/dwt_oracle.c)
+agree with the reference. /root/reference does not exist on the GPU box, so nothing at test time imports
+this file; tests read only the .npz files. Run:  python oracle/make_golden.py
+"""
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+
+from oracle import unet_oracle as O  # noqa: E402
+
+
+def import_reference():
+    """Shims of SURVEY.md 8(c): stub skimage (utils/metrics.py:4), cwd so that the cwd-relative
+    './models/wavelet_weights_c2.pkl' (models/wavelet.py:7) resolves."""
+    for name in ("skimage", "skimage.color"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["skimage"].color = sys.modules["skimage.color"]
+    os.chdir(REF)
+    sys.path.insert(0, REF)
+    import models.unet as ref_unet  # noqa
+    import models.wavelet as ref_wavelet  # noqa
+    import models.ddm_wavelet as ref_ddm  # noqa
+    import utils.sampling as ref_sampling  # noqa
+    import utils.metrics as ref_metrics  # noqa
+    return ref_unet, ref_wavelet, ref_ddm, ref_sampling, ref_metrics
+
+
+def small_cfg():
+    return O.default_config(data__image_size=16, model__ch=64, model__ch_mult=[1, 2], model__num_res_blocks=1,
+                            model__attn_resolutions=[8])
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    ref_unet, ref_wavelet, ref_ddm, ref_sampling, ref_metrics = import_reference()
+
+    # ---------------------------------------------------------------- DWT / IWT
+    import pickle
+    with open(os.path.join(REF, "models", "wavelet_weights_c2.pkl"), "rb") as f:
+        u = pickle._Unpickler(f)
+        u.encoding = "latin1"
+        rec4 = u.load()["rec4"].astype(np.float32)
+    dec = ref_wavelet.WaveletTransform(scale=2, dec=True)
+    rec = ref_wavelet.WaveletTransform(scale=2, dec=False)
+    g = torch.Generator().manual_seed(61)
+    x = torch.randn(2, 3, 8, 12, generator=g)
+    y = torch.randn(2, 48, 3, 5, generator=g)
+    # integer-valued input: every summation order gives the same exactly representable result
+    xi = torch.randint(-64, 64, (1, 3, 12, 8), generator=g).float()
+    with torch.no_grad():
+        ref_y, ref_x, ref_yi = dec(x), rec(y), dec(xi)
+        ref_xi = rec(ref_yi)
+    assert np.array_equal(O.haar_packet_matrix().reshape(16, 16), rec4[:16].reshape(16, 16))
+    assert np.allclose(O.dwt_np(x.numpy()), ref_y.numpy(), atol=2e-6)
+    assert np.allclose(O.iwt_np(y.numpy()), ref_x.numpy(), atol=2e-6)
+    assert np.array_equal(O.dwt_np(xi.numpy()), ref_yi.numpy())
+    np.savez(os.path.join(OUT, "dwt_kat.npz"), rec4=rec4, x=x.numpy(), dwt_x=ref_y.numpy(), y=y.numpy(),
+             iwt_y=ref_x.numpy(), xi=xi.numpy(), dwt_xi=ref_yi.numpy(), iwt_dwt_xi=ref_xi.numpy())
+    print("dwt_kat.npz ok")
+
+    # ---------------------------------------------------------------- UNet, small config
+    cfg = small_cfg()
+    torch.manual_seed(61)
+    net = ref_unet.DiffusionUNet(cfg).eval()
+    sd_ref = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd = O.init_state_dict(cfg, seed=61)
+    assert sorted(sd.keys()) == sorted(sd_ref.keys()), "state-dict keys differ"
+    assert all(torch.equal(sd[k], sd_ref[k]) for k in sd), "init_state_dict is not bit-identical to the reference"
+    g = torch.Generator().manual_seed(62)
+    xin = torch.randn(3, 96, 16, 16, generator=g)
+    t = torch.tensor([37.0, 980.0, 500.0])
+    with torch.no_grad():
+        ref_out = net(xin, t)
+        ora_out = O.unet_forward(sd, cfg, xin, t)
+        ref_out_t1 = net(xin, t[:1])  # the sampler's broadcast-t form (n=1 against P patches)
+    assert torch.equal(ref_out, ora_out), float((ref_out - ora_out).abs().max())
+    wsum = float(sum(v.double().sum() for v in sd.values()))
+    np.savez(os.path.join(OUT, "unet_small.npz"), x=xin.numpy(), t=t.numpy(), out=ref_out.numpy(),
+             out_t1=ref_out_t1.numpy(), weight_sum=np.float64(wsum), seed=61, x_seed=62)
+    print("unet_small.npz ok; weight_sum", wsum)
+
+    # ---------------------------------------------------------------- DDIM sampler, small config
+    stub = types.SimpleNamespace(config=cfg, num_timesteps=1000, device=torch.device("cpu"))
+    betas_np = ref_ddm.get_beta_schedule(beta_schedule="linear", beta_start=1e-4, beta_end=0.02,
+                                         num_diffusion_timesteps=1000)
+    betas = torch.from_numpy(betas_np).float()
+    assert torch.equal(betas, O.beta_schedule(cfg))
+    alphas = ref_sampling.compute_alpha(betas, torch.arange(-1, 1000)).flatten()
+    assert torch.equal(alphas, O.compute_alpha(betas, torch.arange(-1, 1000)).flatten())
+    g = torch.Generator().manual_seed(63)
+    B, h, w, p = 1, 24, 40, 16
+    xc = torch.randn(B, 48, h, w, generator=g)
+    xo = torch.randn(B, 45, h, w, generator=g)
+    x0 = torch.randn(B, 3, h, w, generator=g)
+    h_list, w_list = ref_ddm.DenoisingDiffusion_Wavelet.overlapping_grid_indices(stub, xc, output_size=p, r=8)
+    assert (h_list, w_list) == O.overlapping_grid_indices(h, w, p, 8)
+    corners = [(i, j) for i in h_list for j in w_list]
+    seq = range(0, 1000, 1000 // 6)  # 6 -> skip 166 -> 7 entries: covers len(seq) = S+1 (SURVEY hard parts)
+    with contextlib.redirect_stdout(io.StringIO()):
+        xs, x0p = ref_ddm.DenoisingDiffusion_Wavelet.generalized_steps_overlapping(
+            stub, x0, xc, seq, net, betas, eta=0., corners=corners, p_size=p, x_other=xo, use_other=True)
+    oxs, ox0p = O.ddim_sample_overlapping(lambda a, tt: O.unet_forward(sd, cfg, a, tt), x0, xc, xo, list(seq),
+                                          betas, corners, p)
+    for a, b in zip(xs, oxs):
+        assert torch.equal(a, b)
+    for a, b in zip(x0p, ox0p):
+        assert torch.equal(a, b)
+    np.savez(os.path.join(OUT, "ddim_small.npz"), betas=betas.numpy(), alphas=alphas.numpy(), x_cond=xc.numpy(),
+             x_other=xo.numpy(), x=x0.numpy(), corners=np.array(corners, np.int32), seq=np.array(list(seq)),
+             xs_last=xs[-1].numpy(), x0_preds=torch.stack(x0p).numpy(), xs_1=xs[1].numpy(), p_size=p, r=8)
+    print("ddim_small.npz ok; corners", len(corners), "steps", len(x0p))
+
+    # ---------------------------------------------------------------- UNet, full config, one patch
+    cfgF = O.default_config()
+    torch.manual_seed(61)
+    netF = ref_unet.DiffusionUNet(cfgF).eval()
+    sdF = O.init_state_dict(cfgF, seed=61)
+    assert all(torch.equal(sdF[k], v) for k, v in netF.state_dict().items())
+    nparams = sum(v.numel() for v in sdF.values())
+    assert nparams == 156492675, nparams
+    g = torch.Generator().manual_seed(64)
+    xin = torch.randn(2, 96, 64, 64, generator=g)
+    t = torch.tensor([500.0])
+    with torch.no_grad():
+        ref_out = netF(xin, t)
+        ora_out = O.unet_forward(sdF, cfgF, xin, t)
+    assert torch.equal(ref_out, ora_out)
+    np.savez(os.path.join(OUT, "unet_full.npz"), t=t.numpy(), out=ref_out.numpy(), seed=61, x_seed=64,
+             weight_sum=np.float64(sum(v.double().sum() for v in sdF.values())))
+    print("unet_full.npz ok")
+
+    # ---------------------------------------------------------------- the restore() sandwich, config #1
+    # restoration.py:73-135 with the HFRM bypassed (x_other := HF bands of DWT(gt), the `if 0:` branch at
+    # :99-100), 10 DDIM steps, one 256x256 image -> one 64x64 patch.
+    g = torch.Generator().manual_seed(61)
+    ximg = torch.rand(1, 6, 256, 256, generator=g)
+    noise = torch.randn(1, 3, 64, 64, generator=g)
+    stubF = types.SimpleNamespace(config=cfgF, num_timesteps=1000, device=torch.device("cpu"))
+    with torch.no_grad():
+        xa = 2 * ximg - 1.0
+        x_cond = dec(xa[:, :3].contiguous())
+        x_gt = dec(xa[:, 3:].contiguous())
+        x_other = x_gt[:, 3:]
+        seq = range(0, 1000, 1000 // 10)
+        with contextlib.redirect_stdout(io.StringIO()):
+            xs, x0p = ref_ddm.DenoisingDiffusion_Wavelet.generalized_steps_overlapping(
+                stubF, noise, x_cond, seq, netF, betas, eta=0., corners=[(0, 0)], p_size=64, x_other=x_other,
+                use_other=True)
+        lat = x0p[-5]
+        out = torch.clamp((rec(torch.cat([lat[:, :3], x_other], dim=1)) + 1.0) / 2.0, 0.0, 1.0)
+        psnr = ref_metrics.torchPSNR(ximg[:, 3:], out)
+    np.savez(os.path.join(OUT, "sandwich_full.npz"), seed=61, steps=10, latent_m5=lat.numpy(),
+             out_crop=out[:, :, 96:160, 96:160].numpy(), out_mean=np.float64(out.double().mean()),
+             psnr=np.float32(psnr), xs_last=xs[-1].numpy())
+    print("sandwich_full.npz ok; psnr", float(psnr), "latent range", float(lat.min()), float(lat.max()))
+
+
+if __name__ == "__main__":
+    main()

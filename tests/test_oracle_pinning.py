@@ -1,0 +1,129 @@
+"""CPU: the oracles (oracle/dwt_oracle.c, oracle/unet_oracle.py) against the committed golden vectors that
+oracle/make_golden.py produced from the reference's own modules (the reference ships no tests/fixtures)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import dwt_oracle as DO
+from oracle import unet_oracle as O
+
+
+def test_rec4_closed_form_matches_pickle_weights():
+    g = golden("dwt_kat.npz")
+    assert np.array_equal(DO.rec4(), g["rec4"])
+    assert np.array_equal(O.haar_packet_matrix().reshape(16, 16), g["rec4"][:16].reshape(16, 16))
+
+
+def test_haar_packet_weights_module_layout():
+    from wavedm_b200.wavelet import haar_packet_weights
+    g = golden("dwt_kat.npz")
+    assert np.array_equal(haar_packet_weights(2).numpy(), g["rec4"])
+
+
+@pytest.mark.parametrize("direct", [False, True])
+def test_dwt_oracle_vs_reference_module(direct):
+    g = golden("dwt_kat.npz")
+    y = DO.dwt(g["x"], direct=direct)
+    assert y.shape == g["dwt_x"].shape
+    # tolerance: fp32 summation order of a 16-term dot product of O(1) values (conv backend order unknown)
+    assert np.abs(y - g["dwt_x"]).max() <= 2e-6
+    x = DO.iwt(g["y"], direct=direct)
+    assert np.abs(x - g["iwt_y"]).max() <= 2e-6
+    # integer-valued data: exact in every summation order -> bit-exact layout check
+    assert np.array_equal(DO.dwt(g["xi"], direct=direct), g["dwt_xi"])
+    assert np.array_equal(DO.iwt(g["dwt_xi"], direct=direct), g["iwt_dwt_xi"])
+    assert np.array_equal(g["iwt_dwt_xi"], g["xi"])  # perfect reconstruction on the reference itself
+
+
+def test_dwt_oracle_flags_and_numpy_twin():
+    rng = np.random.default_rng(0)
+    x = rng.random((2, 3, 16, 20), dtype=np.float32)
+    assert np.array_equal(DO.dwt(x, flags=1), DO.dwt(2.0 * x - 1.0))
+    y = DO.dwt(2.0 * x - 1.0)
+    assert np.array_equal(DO.iwt(y, flags=1), np.clip((DO.iwt(y) + 1.0) / 2.0, 0.0, 1.0).astype(np.float32))
+    assert np.abs(O.dwt_np(x) - DO.dwt(x)).max() <= 2e-6
+    assert np.abs(O.iwt_np(y) - DO.iwt(y)).max() <= 4e-6
+    # round trip: orthonormal basis
+    assert np.abs(DO.iwt(DO.dwt(x)) - x).max() <= 1e-6
+    # empty batch
+    assert DO.dwt(np.zeros((0, 3, 8, 8), np.float32)).shape == (0, 48, 2, 2)
+
+
+def test_unet_oracle_small_vs_reference_golden():
+    g = golden("unet_small.npz")
+    cfg = O.default_config(data__image_size=16, model__ch=64, model__ch_mult=[1, 2], model__num_res_blocks=1,
+                           model__attn_resolutions=[8])
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    assert abs(float(sum(v.double().sum() for v in sd.values())) - float(g["weight_sum"])) < 1e-9
+    x, t = torch.from_numpy(g["x"]), torch.from_numpy(g["t"])
+    with torch.no_grad():
+        out = O.unet_forward(sd, cfg, x, t)
+        out1 = O.unet_forward(sd, cfg, x, t[:1])
+    # same torch build + same CPU kernels as the generating run -> equal up to thread-count dependent
+    # reduction order
+    assert (out - torch.from_numpy(g["out"])).abs().max() <= 2e-5
+    assert (out1 - torch.from_numpy(g["out_t1"])).abs().max() <= 2e-5
+
+
+def test_ddim_oracle_small_vs_reference_golden():
+    g = golden("ddim_small.npz")
+    cfg = O.default_config(data__image_size=16, model__ch=64, model__ch_mult=[1, 2], model__num_res_blocks=1,
+                           model__attn_resolutions=[8])
+    betas = O.beta_schedule(cfg)
+    assert np.array_equal(betas.numpy(), g["betas"])
+    assert np.array_equal(O.compute_alpha(betas, torch.arange(-1, 1000)).flatten().numpy(), g["alphas"])
+    assert g["alphas"][0] == 1.0 and abs(g["alphas"][981] - 5.90375e-5) < 1e-9  # SURVEY A.2 samples
+    h, w, p = g["x"].shape[2], g["x"].shape[3], int(g["p_size"])
+    hl, wl = O.overlapping_grid_indices(h, w, p, int(g["r"]))
+    corners = [(i, j) for i in hl for j in wl]
+    assert np.array_equal(np.array(corners, np.int32), g["corners"])
+    assert O.sampling_seq(1000, 6) == list(g["seq"]) and len(g["seq"]) == 7
+    sd = O.init_state_dict(cfg, seed=61)
+    with torch.no_grad():
+        xs, x0p = O.ddim_sample_overlapping(lambda a, tt: O.unet_forward(sd, cfg, a, tt), torch.from_numpy(g["x"]),
+                                            torch.from_numpy(g["x_cond"]), torch.from_numpy(g["x_other"]),
+                                            list(g["seq"]), betas, corners, p)
+    ref = torch.from_numpy(g["x0_preds"])
+    scale = ref.abs().max()
+    assert (torch.stack(x0p) - ref).abs().max() <= 1e-4 * scale
+    assert (xs[-1] - torch.from_numpy(g["xs_last"])).abs().max() <= 1e-4 * scale
+    assert (xs[1] - torch.from_numpy(g["xs_1"])).abs().max() <= 1e-4 * scale
+
+
+def test_grid_indices_cases():
+    # 64^2 -> 1 corner; 128^2 -> 5x5; 120x180 -> 5x9
+    assert O.overlapping_grid_indices(64, 64, 64, 16) == ([0], [0])
+    hl, wl = O.overlapping_grid_indices(128, 128, 64, 16)
+    assert len(hl) == 5 and len(wl) == 5
+    hl, wl = O.overlapping_grid_indices(120, 180, 64, 16)
+    assert (len(hl), len(wl)) == (5, 9) and hl[-1] == 56 and wl[-1] == 116
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference checkout not present")
+def test_oracle_state_dict_is_bit_identical_to_reference_init():
+    """Only in the build container: re-import the reference and compare (what make_golden.py asserts)."""
+    import subprocess, sys
+    code = (
+        "import sys, types, os, torch\n"
+        "for n in ('skimage','skimage.color'): sys.modules.setdefault(n, types.ModuleType(n))\n"
+        "sys.modules['skimage'].color = sys.modules['skimage.color']\n"
+        "repo = sys.argv[1]\n"
+        "sys.path.insert(0, '/root/reference'); os.chdir('/root/reference')\n"
+        "import models.unet as U\n"
+        "sys.path.insert(0, repo)\n"
+        "from oracle import unet_oracle as O\n"
+        "cfg = O.default_config(data__image_size=16, model__ch=64, model__ch_mult=[1, 2], model__num_res_blocks=1, model__attn_resolutions=[8])\n"
+        "torch.manual_seed(7); net = U.DiffusionUNet(cfg)\n"
+        "sd = O.init_state_dict(cfg, seed=7)\n"
+        "ref = net.state_dict()\n"
+        "assert sorted(sd) == sorted(ref)\n"
+        "assert all(torch.equal(sd[k], ref[k]) for k in sd)\n"
+        "x = torch.randn(2, 96, 16, 16); t = torch.tensor([3., 700.])\n"
+        "with torch.no_grad(): assert torch.equal(net(x, t), O.unet_forward(sd, cfg, x, t))\n"
+        "print('OK')\n")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code, repo], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]

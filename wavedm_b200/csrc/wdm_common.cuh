@@ -1,0 +1,52 @@
+// wdm_common.cuh -- shared helpers for the wavedm_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/wavedm_b200.h"
+
+#define WDM_CHECK_CUDA(expr)                                   \
+    do {                                                       \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) return wdm_cuda_error((int)_e); \
+    } while (0)
+
+// CUDA errors are passed through as WDM_ERR_CUDA_BASE - cudaError (always < WDM_ERR_CUDA_BASE).
+static inline int wdm_cuda_error(int e) { return WDM_ERR_CUDA_BASE - e; }
+
+static inline int wdm_launch_status() {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return wdm_cuda_error((int)e);
+    }
+    return WDM_OK;
+}
+
+static inline bool wdm_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+static inline int wdm_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float4 wdm_ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float wdm_ldg_stream(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void wdm_stg_stream(float4* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void wdm_stg_stream(float* p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float wdm_silu(float x) { return x / (1.0f + __expf(-x)); }
+#endif
