@@ -69,6 +69,105 @@ WDM_API const char* wdm_status_string(int status);
 WDM_API int wdm_dwt4x4_fwd(const float* x, float* y, int n, int H, int W, int flags, void* stream);
 WDM_API int wdm_iwt4x4_fwd(const float* y, float* x, int n, int h, int w, int flags, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Conditional diffusion UNet engine.
+ * Replaces  models/unet.py:196-395  (DiffusionUNet.__init__/forward; identical network:
+ * models/unet_wav.py:10-155) with use_window=False, wavelet_in_unet=False: sinusoidal timestep embedding
+ * (:10-28), ResnetBlock (:81-138), AttnBlock (:141-193), Downsample (:59-78), Upsample (:40-56),
+ * GroupNorm(32, eps=1e-6)+SiLU (:31-37).
+ *
+ * Precision modes
+ *   WDM_PREC_FP32 : fp32 storage + fp32 FFMA contractions (parity mode: |d| < 1e-3 per pixel gate)
+ *   WDM_PREC_BF16 : bf16 storage, tcgen05 tensor-core contractions with fp32 accumulation in TMEM,
+ *                   fp32 statistics / softmax / timestep path (throughput mode: PSNR gate)
+ *
+ * Parameters are passed as ONE flat fp32 device buffer holding the reference's state_dict tensors
+ * (models/unet.py state-dict names, OIHW conv weights) concatenated in the canonical order reported by
+ * wdm_unet_param_info(), followed by the extra tensor "temb.freqs" (ch/2 floats, the frequency table of
+ * unet.py:19-21 computed by the host exactly as the reference computes it). wdm_unet_create() re-packs
+ * them into `packed` (caller-allocated, wdm_unet_packed_bytes()) and never touches `flat_params` again.
+ * ------------------------------------------------------------------------------------------------ */
+#define WDM_PREC_FP32 0
+#define WDM_PREC_BF16 1
+/* engine flags (wdm_unet_create) */
+#define WDM_ENGINE_NO_TC 0x1 /* bf16 mode: use the CUDA-core GEMM for every contraction (debug / A-B testing) */
+
+typedef struct wdm_unet_config {
+    int ch;             /* model.ch */
+    int n_levels;       /* len(model.ch_mult) <= 8 */
+    int ch_mult[8];
+    int num_res_blocks; /* model.num_res_blocks */
+    int n_attn_res;     /* len(model.attn_resolutions) <= 8 */
+    int attn_res[8];
+    int resolution;     /* data.image_size (patch side R) */
+    int in_channels;    /* UNet input channels (models/unet.py:212), 96 for raindrop_wavelet.yml */
+    int out_ch;         /* model.out_ch (<= 4) */
+} wdm_unet_config;
+
+typedef struct wdm_unet wdm_unet_t;
+
+WDM_API int wdm_unet_param_count(const wdm_unet_config* cfg);
+/* i-th parameter tensor in canonical order: its state_dict name (NUL-terminated into name[0..cap)) and numel. */
+WDM_API int wdm_unet_param_info(const wdm_unet_config* cfg, int i, char* name, int cap, long long* numel);
+WDM_API size_t wdm_unet_packed_bytes(const wdm_unet_config* cfg, int precision);
+WDM_API int wdm_unet_create(const wdm_unet_config* cfg, int precision, int flags, const float* flat_params,
+                            long long flat_numel, void* packed, size_t packed_bytes, void* stream,
+                            wdm_unet_t** out);
+WDM_API void wdm_unet_destroy(wdm_unet_t* net);
+/* channels of the NHWC input tensor (in_channels rounded up to the engine's K granule) */
+WDM_API int wdm_unet_input_channels_padded(const wdm_unet_t* net);
+WDM_API size_t wdm_unet_workspace_bytes(const wdm_unet_t* net, int P);
+/* x: [P, R, R, Cpad] NHWC in the engine's storage type (as produced by wdm_gather_patches);
+ * t: device fp32 [T], T == 1 (one timestep for all patches, the sampler's case: ddm_wavelet.py:457) or T == P;
+ * eps_out: [P, out_ch, R, R] fp32 NCHW. */
+WDM_API int wdm_unet_forward(wdm_unet_t* net, const void* x, const float* t, int T, int P, float* eps_out,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampler kernels.
+ * wdm_gather_patches replaces the crop + cat of  models/ddm_wavelet.py:467-478  (and the NCHW->NHWC
+ * conversion of the module-level forward): out[p, y, x, c] = concat_s(src_s)[img_p, c, hi_p+y, wi_p+x],
+ * channels >= sum(Cs) zero-filled up to Cpad. srcs are fp32 NCHW [B, Cs, h, w]; patches is device int32
+ * [P][3] = (image, hi, wi). out_dtype: WDM_PREC_FP32 / WDM_PREC_BF16.
+ * wdm_ddim_step replaces  models/ddm_wavelet.py:485-503  (scatter-add of patch outputs, division by the
+ * overlap count, x0 prediction, eta=0 DDIM update) in one kernel; img_first is device int32 [B+1] with the
+ * patch range of every image (patches sorted by image, reference corner order within an image).
+ * ------------------------------------------------------------------------------------------------ */
+WDM_API int wdm_gather_patches(const float* src0, int C0, const float* src1, int C1, const float* src2, int C2, int B,
+                               int h, int w, const int* patches, int P, int R, int Cpad, void* out, int out_dtype,
+                               void* stream);
+WDM_API int wdm_ddim_step(const float* eps, const int* patches, const int* img_first, int P, int B, int Cp, int R,
+                          int h, int w, const float* xt, float* x0_out, float* xt_next, float at, float at_next,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-kernel entry points (unit tests / micro-benchmarks). Semantics in csrc/wdm_engine.h.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct wdm_gemm_params {
+    const void* src0;
+    const void* src1;
+    int C0, C1, ld0, ld1, Hin, Win, Hout, Wout, taps, stride, pad, ups;
+    const void* B;
+    long long b_batch_stride;
+    int ldb, b_layout, M, N, K;
+    float alpha;
+    const float* bias;
+    const float* temb;
+    int temb_rows, temb_ld;
+    const void* residual;
+    int ldr;
+    void* out;
+    int ldo, a_dtype, b_dtype, out_dtype;
+} wdm_gemm_params;
+#define WDM_GEMM_IMPL_SIMT 0
+#define WDM_GEMM_IMPL_TC 1
+WDM_API int wdm_gemm(const wdm_gemm_params* p, int impl, void* stream);
+WDM_API size_t wdm_groupnorm_scratch_bytes(int P);
+WDM_API int wdm_groupnorm_silu(const void* src0, int C0, const void* src1, int C1, int dtype, int P, int HW,
+                               float eps, const float* gamma, const float* beta, int silu, void* out,
+                               void* scratch, void* stream);
+WDM_API int wdm_softmax_rows(const float* S, int rows, int L, void* out, int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

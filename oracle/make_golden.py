@@ -51,7 +51,7 @@ def import_reference():
 
 
 def small_cfg():
-    return O.default_config(data__image_size=16, model__ch=64, model__ch_mult=[1, 2], model__num_res_blocks=1,
+    return O.default_config(data__image_size=16, model__ch=128, model__ch_mult=[1, 2], model__num_res_blocks=1,
                             model__attn_resolutions=[8])
 
 

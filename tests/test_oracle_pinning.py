@@ -54,7 +54,7 @@ def test_dwt_oracle_flags_and_numpy_twin():
 
 def test_unet_oracle_small_vs_reference_golden():
     g = golden("unet_small.npz")
-    cfg = O.default_config(data__image_size=16, model__ch=64, model__ch_mult=[1, 2], model__num_res_blocks=1,
+    cfg = O.default_config(data__image_size=16, model__ch=128, model__ch_mult=[1, 2], model__num_res_blocks=1,
                            model__attn_resolutions=[8])
     sd = O.init_state_dict(cfg, seed=int(g["seed"]))
     assert abs(float(sum(v.double().sum() for v in sd.values())) - float(g["weight_sum"])) < 1e-9
@@ -70,7 +70,7 @@ def test_unet_oracle_small_vs_reference_golden():
 
 def test_ddim_oracle_small_vs_reference_golden():
     g = golden("ddim_small.npz")
-    cfg = O.default_config(data__image_size=16, model__ch=64, model__ch_mult=[1, 2], model__num_res_blocks=1,
+    cfg = O.default_config(data__image_size=16, model__ch=128, model__ch_mult=[1, 2], model__num_res_blocks=1,
                            model__attn_resolutions=[8])
     betas = O.beta_schedule(cfg)
     assert np.array_equal(betas.numpy(), g["betas"])
@@ -115,7 +115,7 @@ def test_oracle_state_dict_is_bit_identical_to_reference_init():
         "import models.unet as U\n"
         "sys.path.insert(0, repo)\n"
         "from oracle import unet_oracle as O\n"
-        "cfg = O.default_config(data__image_size=16, model__ch=64, model__ch_mult=[1, 2], model__num_res_blocks=1, model__attn_resolutions=[8])\n"
+        "cfg = O.default_config(data__image_size=16, model__ch=128, model__ch_mult=[1, 2], model__num_res_blocks=1, model__attn_resolutions=[8])\n"
         "torch.manual_seed(7); net = U.DiffusionUNet(cfg)\n"
         "sd = O.init_state_dict(cfg, seed=7)\n"
         "ref = net.state_dict()\n"

@@ -1,0 +1,223 @@
+"""GPU parity of the UNet engine and its kernels against the torch-fp32 oracle (oracle/unet_oracle.py, itself
+pinned to the reference module by tests/golden/*) -- through the C ABI."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden
+from oracle import unet_oracle as O
+from wavedm_b200 import _lib, engine
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+def small_cfg():
+    return O.default_config(data__image_size=16, model__ch=128, model__ch_mult=[1, 2], model__num_res_blocks=1,
+                            model__attn_resolutions=[8])
+
+
+class GemmParams(ctypes.Structure):
+    _fields_ = [("src0", ctypes.c_void_p), ("src1", ctypes.c_void_p)] + \
+        [(n, ctypes.c_int) for n in ("C0", "C1", "ld0", "ld1", "Hin", "Win", "Hout", "Wout", "taps", "stride", "pad", "ups")] + \
+        [("B", ctypes.c_void_p), ("b_batch_stride", ctypes.c_longlong)] + \
+        [(n, ctypes.c_int) for n in ("ldb", "b_layout", "M", "N", "K")] + \
+        [("alpha", ctypes.c_float), ("bias", ctypes.c_void_p), ("temb", ctypes.c_void_p), ("temb_rows", ctypes.c_int),
+         ("temb_ld", ctypes.c_int), ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int), ("out", ctypes.c_void_p)] + \
+        [(n, ctypes.c_int) for n in ("ldo", "a_dtype", "b_dtype", "out_dtype")]
+
+
+def run_conv(x, x2, w, bias, stride, ups, temb, residual, dtype, impl):
+    """x, x2: NCHW fp32 torch (cpu); w OIHW. Runs the C-ABI gemm on NHWC tensors, returns NCHW fp32."""
+    lib = _lib.load()
+    td = torch.float32 if dtype == 0 else torch.bfloat16
+    P, C0, H, W = x.shape
+    C1 = 0 if x2 is None else x2.shape[1]
+    Cout, Cin, k, _ = w.shape
+    taps = k * k
+    Hout, Wout = (H * 2, W * 2) if ups else ((H // 2, W // 2) if stride == 2 else (H, W))
+    xa = x.permute(0, 2, 3, 1).contiguous().to(DEV, td)
+    xb = None if x2 is None else x2.permute(0, 2, 3, 1).contiguous().to(DEV, td)
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, taps * Cin).contiguous().to(DEV, td)
+    out = torch.empty(P, Hout, Wout, Cout, device=DEV, dtype=td)
+    p = GemmParams()
+    p.src0, p.C0, p.ld0 = xa.data_ptr(), C0, C0
+    if xb is not None:
+        p.src1, p.C1, p.ld1 = xb.data_ptr(), C1, C1
+    p.Hin, p.Win, p.Hout, p.Wout = H, W, Hout, Wout
+    p.taps, p.stride, p.pad, p.ups = taps, stride, (1 if taps == 9 and stride == 1 else 0), ups
+    p.B, p.ldb, p.b_layout = wp.data_ptr(), taps * Cin, 0
+    p.M, p.N, p.K = P * Hout * Wout, Cout, taps * Cin
+    p.alpha = 1.0
+    keep = [xa, xb, wp]
+    if bias is not None:
+        b = bias.to(DEV)
+        keep.append(b)
+        p.bias = b.data_ptr()
+    if temb is not None:
+        tb = temb.contiguous().to(DEV)
+        keep.append(tb)
+        p.temb, p.temb_rows, p.temb_ld = tb.data_ptr(), tb.shape[0], tb.shape[1]
+    if residual is not None:
+        r = residual.permute(0, 2, 3, 1).contiguous().to(DEV, td)
+        keep.append(r)
+        p.residual, p.ldr = r.data_ptr(), Cout
+    p.out, p.ldo = out.data_ptr(), Cout
+    p.a_dtype = p.b_dtype = p.out_dtype = dtype
+    st = lib.wdm_gemm(ctypes.byref(p), impl, torch.cuda.current_stream().cuda_stream)
+    _lib.check(st, "wdm_gemm")
+    torch.cuda.synchronize()
+    return out.float().permute(0, 3, 1, 2).cpu()
+
+
+def ref_conv(x, x2, w, bias, stride, ups, temb, residual):
+    xx = x if x2 is None else torch.cat([x, x2], 1)
+    if ups:
+        xx = F.interpolate(xx, scale_factor=2.0, mode="nearest")
+    k = w.shape[2]
+    if stride == 2:
+        y = F.conv2d(F.pad(xx, (0, 1, 0, 1)), w, bias, stride=2)
+    else:
+        y = F.conv2d(xx, w, bias, padding=k // 2)
+    if temb is not None:
+        t = temb if temb.shape[0] > 1 else temb.expand(x.shape[0], -1)
+        y = y + t[:, :, None, None]
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+CONV_CASES = [
+    # P, C0, C1, Cout, H, k, stride, ups, temb_rows, residual
+    (2, 128, 0, 128, 16, 3, 1, 0, 0, False),
+    (3, 96, 0, 128, 16, 3, 1, 0, 1, False),     # conv_in-like K, broadcast temb
+    (2, 128, 128, 256, 8, 3, 1, 0, 2, True),    # concat + per-patch temb + residual
+    (2, 256, 128, 128, 8, 1, 1, 0, 0, True),    # nin_shortcut over a concat
+    (2, 128, 0, 128, 16, 3, 2, 0, 0, False),    # downsample (pad right/bottom)
+    (2, 128, 0, 128, 8, 3, 1, 1, 0, False),     # upsample folded into addressing
+    (1, 256, 0, 768, 8, 3, 1, 0, 0, False),     # N not a multiple of 128*k tile edge
+    (5, 128, 0, 256, 4, 1, 1, 0, 0, False),     # M = 80: partial M tile
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_gemm_simt_fp32_conv_cases(case):
+    P, C0, C1, Cout, H, k, stride, ups, trows, has_res = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(P, C0, H, H, generator=g)
+    x2 = torch.randn(P, C1, H, H, generator=g) if C1 else None
+    w = torch.randn(Cout, C0 + C1, k, k, generator=g) / (k * (C0 + C1) ** 0.5)
+    bias = torch.randn(Cout, generator=g)
+    temb = torch.randn(trows, Cout, generator=g) if trows else None
+    Ho = H * 2 if ups else (H // 2 if stride == 2 else H)
+    res = torch.randn(P, Cout, Ho, Ho, generator=g) if has_res else None
+    ref = ref_conv(x, x2, w, bias, stride, ups, temb, res)
+    out = run_conv(x, x2, w, bias, stride, ups, temb, res, 0, _lib.WDM_GEMM_IMPL_SIMT)
+    # fp32 FFMA vs MKL-DNN: summation-order differences only
+    assert (out - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+    outb = run_conv(x, x2, w, bias, stride, ups, temb, res, 1, _lib.WDM_GEMM_IMPL_SIMT)
+    # bf16 storage: inputs/outputs rounded to 8 mantissa bits
+    assert (outb - ref).abs().max().item() <= 4e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("shape", [(3, 128, 0, 64), (2, 256, 128, 16), (2, 768, 768, 64), (1, 1280, 0, 256), (2, 512, 0, 256)])
+def test_groupnorm_silu(dtype, shape):
+    P, C0, C1, HW = shape
+    lib = _lib.load()
+    td = torch.float32 if dtype == 0 else torch.bfloat16
+    g = torch.Generator().manual_seed(3)
+    a = (torch.randn(P, HW, C0, generator=g) * 3 + 1.5).to(td)
+    b = (torch.randn(P, HW, C1, generator=g) - 2).to(td) if C1 else None
+    C = C0 + C1
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    full = a.float() if b is None else torch.cat([a.float(), b.float()], 2)
+    for silu in (0, 1):
+        ref = F.group_norm(full.permute(0, 2, 1).reshape(P, C, HW, 1), 32, gamma, beta, eps=1e-6)
+        if silu:
+            ref = ref * torch.sigmoid(ref)
+        ref = ref.reshape(P, C, HW).permute(0, 2, 1)
+        ad, bd = a.to(DEV), (b.to(DEV) if b is not None else None)
+        out = torch.empty(P, HW, C, device=DEV, dtype=td)
+        scratch = torch.empty(lib.wdm_groupnorm_scratch_bytes(P), dtype=torch.uint8, device=DEV)
+        gd, bed = gamma.to(DEV), beta.to(DEV)
+        st = lib.wdm_groupnorm_silu(ad.data_ptr(), C0, bd.data_ptr() if bd is not None else None, C1, dtype, P, HW, 1e-6,
+                                    gd.data_ptr(), bed.data_ptr(), silu, out.data_ptr(), scratch.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "wdm_groupnorm_silu")
+        err = (out.float().cpu() - ref).abs().max().item()
+        assert err <= (2e-5 if dtype == 0 else 6e-2), err
+
+
+def test_softmax_rows():
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(4)
+    for L in (64, 256):
+        S = torch.randn(37, L, generator=g) * 4
+        out = torch.empty(37, L, device=DEV)
+        Sd = S.to(DEV)
+        _lib.check(lib.wdm_softmax_rows(Sd.data_ptr(), 37, L, out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream), "softmax")
+        assert (out.cpu() - torch.softmax(S, 1)).abs().max().item() <= 1e-6
+
+
+def _engine(cfg, sd, precision, flags=0):
+    return engine.UNetEngine(cfg, sd, DEV, precision=precision, flags=flags)
+
+
+def test_unet_small_fp32_vs_reference_golden():
+    g = golden("unet_small.npz")
+    cfg = small_cfg()
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    eng = _engine(cfg, sd, "fp32")
+    x, t = torch.from_numpy(g["x"]), torch.from_numpy(g["t"])
+    out = eng.forward(x.to(DEV), t.to(DEV)).cpu()
+    ref = torch.from_numpy(g["out"])
+    assert out.shape == ref.shape
+    err = (out - ref).abs().max().item()
+    assert err <= 5e-5 * max(1.0, ref.abs().max().item()), err
+    out1 = eng.forward(x.to(DEV), t[:1].to(DEV)).cpu()  # broadcast-t form used by the sampler
+    assert (out1 - torch.from_numpy(g["out_t1"])).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_unet_small_bf16_simt_vs_oracle():
+    g = golden("unet_small.npz")
+    cfg = small_cfg()
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    eng = _engine(cfg, sd, "bf16", flags=_lib.WDM_ENGINE_NO_TC)
+    x, t = torch.from_numpy(g["x"]), torch.from_numpy(g["t"])
+    out = eng.forward(x.to(DEV), t.to(DEV)).cpu()
+    ref = torch.from_numpy(g["out"])
+    rel = ((out - ref).norm() / ref.norm()).item()
+    assert rel <= 3e-2, rel
+
+
+def test_unet_full_fp32_vs_reference_golden():
+    g = golden("unet_full.npz")
+    cfg = O.default_config()
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    assert abs(float(sum(v.double().sum() for v in sd.values())) - float(g["weight_sum"])) < 1e-6
+    eng = _engine(cfg, sd, "fp32")
+    gen = torch.Generator().manual_seed(int(g["x_seed"]))
+    x = torch.randn(2, 96, 64, 64, generator=gen)
+    out = eng.forward(x.to(DEV), torch.from_numpy(g["t"]).to(DEV)).cpu()
+    ref = torch.from_numpy(g["out"])
+    err = (out - ref).abs().max().item()
+    assert err <= 5e-5 * max(1.0, ref.abs().max().item()), err
+
+
+def test_workspace_too_small_is_reported():
+    cfg = small_cfg()
+    sd = O.init_state_dict(cfg, seed=1)
+    eng = _engine(cfg, sd, "fp32")
+    x = torch.zeros(2, 16, 16, eng.cin_pad, device=DEV)
+    t = torch.zeros(1, device=DEV)
+    out = torch.empty(2, 3, 16, 16, device=DEV)
+    ws = torch.empty(1 << 16, dtype=torch.uint8, device=DEV)
+    wp = (ws.data_ptr() + 1023) // 1024 * 1024
+    st = eng.lib.wdm_unet_forward(eng.handle, x.data_ptr(), t.data_ptr(), 1, 2, out.data_ptr(), wp, 4096, None)
+    assert st == _lib.WDM_ERR_WORKSPACE
+    with pytest.raises(KeyError):
+        engine.UNetEngine(cfg, {k: v for k, v in sd.items() if k != "conv_in.bias"}, DEV, precision="fp32")

@@ -31,6 +31,11 @@ WDM_IWT_POST_CLAMP = 0x1
 WDM_WT_IMPL_AUTO = 0x00
 WDM_WT_IMPL_DIRECT = 0x10
 WDM_WT_IMPL_TMA = 0x20
+WDM_PREC_FP32 = 0
+WDM_PREC_BF16 = 1
+WDM_ENGINE_NO_TC = 0x1
+WDM_GEMM_IMPL_SIMT = 0
+WDM_GEMM_IMPL_TC = 1
 
 
 class WdmError(RuntimeError):
@@ -63,14 +68,33 @@ def load() -> ctypes.CDLL:
             "(or `make -C wavedm_b200/csrc`). wavedm_b200 has no CPU / PyTorch fallback.")
     lib = ctypes.CDLL(LIB_PATH)
     c_int, c_void_p, c_char_p, c_size_t = ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t
+    c_longlong, c_float = ctypes.c_longlong, ctypes.c_float
     sigs: Dict[str, tuple] = {
         "wdm_version": (c_int, []),
         "wdm_build_arch": (c_char_p, []),
         "wdm_status_string": (c_char_p, [c_int]),
         "wdm_dwt4x4_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
         "wdm_iwt4x4_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+        "wdm_unet_param_count": (c_int, [c_void_p]),
+        "wdm_unet_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, c_void_p]),
+        "wdm_unet_packed_bytes": (c_size_t, [c_void_p, c_int]),
+        "wdm_unet_create": (c_int, [c_void_p, c_int, c_int, c_void_p, c_longlong, c_void_p, c_size_t, c_void_p,
+                                    c_void_p]),
+        "wdm_unet_destroy": (None, [c_void_p]),
+        "wdm_unet_input_channels_padded": (c_int, [c_void_p]),
+        "wdm_unet_workspace_bytes": (c_size_t, [c_void_p, c_int]),
+        "wdm_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
+        "wdm_gather_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                       c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+        "wdm_ddim_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_float, c_float, c_void_p]),
+        "wdm_gemm": (c_int, [c_void_p, c_int, c_void_p]),
+        "wdm_groupnorm_scratch_bytes": (c_size_t, [c_int]),
+        "wdm_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                       c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+        "wdm_softmax_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     }
-    _ = c_size_t
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -346,8 +346,8 @@ int set_smem(K kernel) {
 }
 
 int wt_common_checks(const void* a, const void* b, int n, int H, int W, int flags, int flag_mask) {
-    if (!a || !b) return WDM_ERR_BAD_ARG;
     if (n < 0 || H < 0 || W < 0) return WDM_ERR_BAD_SHAPE;
+    if ((!a || !b) && n != 0 && H != 0 && W != 0) return WDM_ERR_BAD_ARG;
     if ((H % 4) || (W % 4)) return WDM_ERR_BAD_SHAPE;
     if (flags & ~(flag_mask | WDM_WT_IMPL_MASK)) return WDM_ERR_BAD_ARG;
     const int impl = flags & WDM_WT_IMPL_MASK;

@@ -1,0 +1,523 @@
+// wdm_elem.cu -- the HBM-bound / small kernels around the contractions:
+//   GroupNorm statistics + normalise/affine/SiLU (models/unet.py:36-37,31-33), row softmax (unet.py:182),
+//   nearest x2 upsample (unet.py:52-53), timestep embedding + temb projections (unet.py:10-28,354-357,125),
+//   patch gather (ddm_wavelet.py:467-478), fused overlap-average + DDIM update (ddm_wavelet.py:485-503),
+//   weight packing.
+#include "wdm_common.cuh"
+#include "wdm_engine.h"
+
+namespace wdm {
+namespace {
+
+// ---------------------------------------------------------------------------------------------- helpers
+template <typename T, int V>
+struct Vec;
+template <>
+struct Vec<float, 4> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        float4 a = *reinterpret_cast<const float4*>(p);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <>
+struct Vec<float, 8> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+        float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *(reinterpret_cast<float4*>(p) + 1) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+template <>
+struct Vec<__nv_bfloat16, 4> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+        uint2 q = *reinterpret_cast<const uint2*>(p);
+        v[0] = __uint_as_float(q.x << 16), v[1] = __uint_as_float(q.x & 0xffff0000u);
+        v[2] = __uint_as_float(q.y << 16), v[3] = __uint_as_float(q.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+        uint2 q;
+        q.x = pack_bf16(v[0], v[1]), q.y = pack_bf16(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = q;
+    }
+};
+template <>
+struct Vec<__nv_bfloat16, 8> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        uint4 q = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[2 * i] = __uint_as_float(w[i] << 16), v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint4 q;
+        q.x = pack_bf16(v[0], v[1]), q.y = pack_bf16(v[2], v[3]), q.z = pack_bf16(v[4], v[5]), q.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p) = q;
+    }
+};
+
+template <typename T>
+struct AccT {
+    typedef double type;  // fp32 engine: double statistics (sum / sum of squares without cancellation)
+};
+template <>
+struct AccT<__nv_bfloat16> {
+    typedef float type;
+};
+
+__device__ __forceinline__ float silu_precise(float x) { return x * (1.0f / (1.0f + expf(-x))); }
+
+constexpr int kMaxSlabs = 32;
+
+// ---------------------------------------------------------------------------------------------- GroupNorm
+// grid (S, P); block = ppi * nvec threads (thread = fixed V-channel vector, ppi pixels in flight).
+// partial[p][s][g] = (sum, sumsq) in double.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ s0, int C0, const T* __restrict__ s1,
+                                                       int C1, int HW, int S, double2* __restrict__ partial) {
+    __shared__ double red[32][2];
+    const int C = C0 + C1, nvec = C / V, cpg = C / 32;
+    const int p = blockIdx.y, s = blockIdx.x;
+    const int vec = threadIdx.x % nvec, lane_pix = threadIdx.x / nvec, ppi = blockDim.x / nvec;
+    const int c = vec * V, g = c / cpg;
+    if (threadIdx.x < 64) red[threadIdx.x >> 1][threadIdx.x & 1] = 0.0;
+    __syncthreads();
+    const int pix_per_slab = HW / S;
+    const int px0 = s * pix_per_slab, px1 = px0 + pix_per_slab;
+    const T* base;
+    int ld, co;
+    if (c < C0)
+        base = s0, ld = C0, co = c;
+    else
+        base = s1, ld = C1, co = c - C0;
+    base += (long long)p * HW * ld + co;
+    typename AccT<T>::type sum = 0, sq = 0;
+    for (int px = px0 + lane_pix; px < px1; px += ppi) {
+        float v[V];
+        Vec<T, V>::load(base + (long long)px * ld, v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            sum += v[i];
+            sq += (typename AccT<T>::type)v[i] * v[i];
+        }
+    }
+    atomicAdd(&red[g][0], (double)sum);
+    atomicAdd(&red[g][1], (double)sq);
+    __syncthreads();
+    if (threadIdx.x < 32) partial[((long long)p * S + s) * 32 + threadIdx.x] = make_double2(red[threadIdx.x][0], red[threadIdx.x][1]);
+}
+
+// Finalise partial sums -> (mean, rstd) per (p, g). One thread per (p, g).
+__global__ void gn_finalize_kernel(const double2* __restrict__ partial, int S, int n_pg, double inv_n, double eps,
+                                   float* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pg) return;
+    const int p = i / 32, g = i % 32;
+    double sum = 0, sq = 0;
+    for (int s = 0; s < S; ++s) {
+        double2 t = partial[((long long)p * S + s) * 32 + g];
+        sum += t.x, sq += t.y;
+    }
+    const double mean = sum * inv_n;
+    double var = sq * inv_n - mean * mean;
+    if (var < 0) var = 0;
+    stats[2 * i] = (float)mean;
+    stats[2 * i + 1] = (float)(1.0 / sqrt(var + eps));
+}
+
+template <typename T, int V, bool kSilu, bool kPrecise>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0, int C0, const T* __restrict__ s1,
+                                                       int C1, int HW, int pix_per_cta,
+                                                       const float* __restrict__ stats,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, T* __restrict__ out) {
+    const int C = C0 + C1, nvec = C / V, cpg = C / 32;
+    const int p = blockIdx.y;
+    const int vec = threadIdx.x % nvec, lane_pix = threadIdx.x / nvec, ppi = blockDim.x / nvec;
+    const int c = vec * V, g = c / cpg;
+    const float mean = stats[(p * 32 + g) * 2], rstd = stats[(p * 32 + g) * 2 + 1];
+    float a[V], b[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        a[i] = rstd * gamma[c + i];
+        b[i] = beta[c + i] - mean * a[i];
+    }
+    const T* base;
+    int ld, co;
+    if (c < C0)
+        base = s0, ld = C0, co = c;
+    else
+        base = s1, ld = C1, co = c - C0;
+    base += (long long)p * HW * ld + co;
+    T* o = out + (long long)p * HW * C + c;
+    const int px0 = blockIdx.x * pix_per_cta;
+    const int px1 = min(HW, px0 + pix_per_cta);
+    for (int px = px0 + lane_pix; px < px1; px += ppi) {
+        float v[V];
+        Vec<T, V>::load(base + (long long)px * ld, v);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            float y = fmaf(v[i], a[i], b[i]);
+            if (kSilu) y = kPrecise ? silu_precise(y) : wdm_silu(y);
+            v[i] = y;
+        }
+        Vec<T, V>::store(o + (long long)px * C, v);
+    }
+}
+
+struct GnGeom {
+    int V, nvec, threads;
+};
+inline bool gn_geom(int C0, int C1, GnGeom* g) {
+    const int C = C0 + C1;
+    if (C % 32) return false;
+    int V = 4;
+    if (C / 4 > 256) V = 8;
+    if ((C % V) || (C0 % V) || ((C / 32) % V) || C / V > 256) return false;
+    g->V = V;
+    g->nvec = C / V;
+    g->threads = (256 / g->nvec) * g->nvec;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------- upsample
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ src, int P, int H, int W, int C8, T* __restrict__ out) {
+    // one thread per 16-byte vector of the OUTPUT
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)P * 4 * H * W * C8;
+    if (i >= total) return;
+    const int cv = (int)(i % C8);
+    long long r = i / C8;
+    const int ox = (int)(r % (2 * W));
+    r /= (2 * W);
+    const int oy = (int)(r % (2 * H));
+    const int p = (int)(r / (2 * H));
+    const uint4* s = reinterpret_cast<const uint4*>(src) + (((long long)p * H + (oy >> 1)) * W + (ox >> 1)) * C8 + cv;
+    reinterpret_cast<uint4*>(out)[i] = __ldg(s);
+}
+
+// ---------------------------------------------------------------------------------------------- softmax
+// one warp per row, L <= 1024, L % 32 == 0
+template <typename TO>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, long long rows, int L,
+                                                           TO* __restrict__ out) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* s = S + row * L;
+    float v[32];
+    const int n = L >> 5;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (i < n) {
+            v[i] = s[i * 32 + lane];
+            mx = fmaxf(mx, v[i]);
+        }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (i < n) {
+            v[i] = expf(v[i] - mx);
+            sum += v[i];
+        }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    TO* d = out + row * L;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (i < n) {
+            const float y = v[i] / sum;
+            if (sizeof(TO) == 4)
+                reinterpret_cast<float*>(d)[i * 32 + lane] = y;
+            else
+                reinterpret_cast<__nv_bfloat16*>(d)[i * 32 + lane] = __float2bfloat16(y);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------- temb
+// out[t][n] = act( sum_k in[t][k] * W[n][k] + b[n] ); one warp per (t, n).
+// mode 0: in = sinusoidal embedding of t computed on the fly from freqs (K = 2*half)
+// act_silu: apply SiLU to the OUTPUT (the consumers all take silu(.) of it)
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ in, const float* __restrict__ tvals,
+                                                     const float* __restrict__ freqs, int half,
+                                                     const float* __restrict__ W, const float* __restrict__ b, int T,
+                                                     int N, int K, int act_silu, float* __restrict__ out) {
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= (long long)T * N) return;
+    const int t = (int)(wid / N), n = (int)(wid % N);
+    const int lane = threadIdx.x & 31;
+    const float* w = W + (long long)n * K;
+    float acc = 0.f;
+    if (tvals) {
+        const float tv = tvals[t];
+        for (int k = lane; k < K; k += 32) {
+            float e;
+            if (k < half)
+                e = sinf(__fmul_rn(tv, freqs[k]));
+            else if (k < 2 * half)
+                e = cosf(__fmul_rn(tv, freqs[k - half]));
+            else
+                e = 0.f;
+            acc = fmaf(e, w[k], acc);
+        }
+    } else {
+        const float* x = in + (long long)t * K;
+        for (int k = lane; k < K; k += 32) acc = fmaf(x[k], w[k], acc);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        float y = acc + b[n];
+        if (act_silu) y = silu_precise(y);
+        out[(long long)t * N + n] = y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- gather
+// grid (R rows, P patches); smem tile [Cpad][R+1]
+template <typename TO>
+__global__ void __launch_bounds__(256) gather_patches_kernel(const GatherParams p) {
+    extern __shared__ float tile[];
+    const int y = blockIdx.x, pi = blockIdx.y;
+    const int R = p.R, Cpad = p.Cpad, pitch = R + 1;
+    const int img = p.patches[pi * 3], hi = p.patches[pi * 3 + 1], wi = p.patches[pi * 3 + 2];
+    const int c01 = p.Cs[0] + p.Cs[1];
+    const int ctot = c01 + (p.nsrc > 2 ? p.Cs[2] : 0);
+    for (int i = threadIdx.x; i < Cpad * R; i += blockDim.x) {
+        const int c = i / R, x = i - c * R;
+        float v = 0.f;
+        if (c < ctot) {
+            const float* s;
+            int cs, Cs;
+            if (c < p.Cs[0])
+                s = p.src[0], cs = c, Cs = p.Cs[0];
+            else if (c < c01)
+                s = p.src[1], cs = c - p.Cs[0], Cs = p.Cs[1];
+            else
+                s = p.src[2], cs = c - c01, Cs = p.Cs[2];
+            v = __ldg(s + (((long long)img * Cs + cs) * p.h + (hi + y)) * p.w + (wi + x));
+        }
+        tile[c * pitch + x] = v;
+    }
+    __syncthreads();
+    TO* o = reinterpret_cast<TO*>(p.out) + ((long long)pi * R + y) * R * Cpad;
+    for (int j = threadIdx.x; j < R * Cpad; j += blockDim.x) {
+        const int x = j / Cpad, c = j - x * Cpad;
+        const float v = tile[c * pitch + x];
+        if (sizeof(TO) == 4)
+            reinterpret_cast<float*>(o)[j] = v;
+        else
+            reinterpret_cast<__nv_bfloat16*>(o)[j] = __float2bfloat16(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- DDIM step
+// One thread per image element. Every arithmetic step is an explicitly rounded fp32 op in the order torch
+// eager evaluates models/ddm_wavelet.py:496-502 (no FMA contraction) so the update is bit-identical to
+// the oracle given the same eps.
+__global__ void __launch_bounds__(256) ddim_step_kernel(const DdimParams p) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)p.B * p.Cp * p.h * p.w;
+    if (i >= total) return;
+    const int x = (int)(i % p.w);
+    long long r = i / p.w;
+    const int y = (int)(r % p.h);
+    r /= p.h;
+    const int c = (int)(r % p.Cp);
+    const int b = (int)(r / p.Cp);
+    float sum = 0.f;
+    float cnt = 0.f;
+    const int q0 = p.img_first[b], q1 = p.img_first[b + 1];
+    for (int q = q0; q < q1; ++q) {
+        const int hi = p.patches[q * 3 + 1], wi = p.patches[q * 3 + 2];
+        const int py = y - hi, px = x - wi;
+        if (py >= 0 && py < p.R && px >= 0 && px < p.R) {
+            sum = __fadd_rn(sum, p.eps[(((long long)q * p.Cp + c) * p.R + py) * p.R + px]);
+            cnt += 1.f;
+        }
+    }
+    const float et = __fdiv_rn(sum, cnt);
+    const float xt = p.xt[i];
+    const float s1 = __fsqrt_rn(__fsub_rn(1.0f, p.at));
+    const float x0 = __fdiv_rn(__fsub_rn(xt, __fmul_rn(et, s1)), __fsqrt_rn(p.at));
+    p.x0_out[i] = x0;
+    const float c2 = __fsqrt_rn(__fsub_rn(1.0f, p.at_next));
+    // at_next.sqrt()*x0 + c1*randn (c1 = 0 for eta = 0) + c2*et
+    const float xn = __fadd_rn(__fadd_rn(__fmul_rn(__fsqrt_rn(p.at_next), x0), 0.0f), __fmul_rn(c2, et));
+    p.xt_next[i] = xn;
+}
+
+// ---------------------------------------------------------------------------------------------- packing
+template <typename TO>
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int Cin_pad,
+                                        TO* __restrict__ out, long long ldk, long long k_off) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)Cout * taps * Cin_pad;
+    if (i >= total) return;
+    const int ci = (int)(i % Cin_pad);
+    long long r = i / Cin_pad;
+    const int tap = (int)(r % taps);
+    const int co = (int)(r / taps);
+    const float v = ci < Cin ? w[((long long)co * Cin + ci) * taps + tap] : 0.f;
+    TO* d = out + (long long)co * ldk + k_off + (long long)tap * Cin_pad + ci;
+    if (sizeof(TO) == 4)
+        *reinterpret_cast<float*>(d) = v;
+    else
+        *reinterpret_cast<__nv_bfloat16*>(d) = __float2bfloat16(v);
+}
+
+}  // namespace
+
+// ================================================================================================ launchers
+static int pick_slabs(int P, int HW) {
+    int S = 1;
+    while (S < kMaxSlabs && P * S < 2 * 148 && HW / (S * 2) >= 16 && HW % (S * 2) == 0) S *= 2;
+    return S;
+}
+
+size_t gn_partial_bytes(int P) { return (size_t)P * kMaxSlabs * 32 * sizeof(double2); }
+
+int launch_gn_stats(const void* src0, int C0, const void* src1, int C1, int dtype, int P, int HW, float eps,
+                    float* stats, cudaStream_t s) {
+    // `stats` buffer layout: [P*32*2 floats (mean, rstd)] followed (256-byte aligned) by the double2 partials.
+    GnGeom g;
+    if (!gn_geom(C0, C1, &g)) return WDM_ERR_BAD_SHAPE;
+    const int S = pick_slabs(P, HW);
+    double2* partial = reinterpret_cast<double2*>(reinterpret_cast<char*>(stats) + (((size_t)P * 64 * 4 + 255) & ~(size_t)255));
+    dim3 grid(S, P);
+#define WDM_GN_STATS(T, V)                                                                                     \
+    gn_stats_kernel<T, V><<<grid, g.threads, 0, s>>>(reinterpret_cast<const T*>(src0), C0,                      \
+                                                     reinterpret_cast<const T*>(src1), C1, HW, S, partial)
+    if (dtype == DT_F32) {
+        if (g.V == 4) WDM_GN_STATS(float, 4); else WDM_GN_STATS(float, 8);
+    } else {
+        if (g.V == 4) WDM_GN_STATS(__nv_bfloat16, 4); else WDM_GN_STATS(__nv_bfloat16, 8);
+    }
+#undef WDM_GN_STATS
+    int st = wdm_launch_status();
+    if (st != WDM_OK) return st;
+    const int n_pg = P * 32;
+    const double inv_n = 1.0 / ((double)HW * ((C0 + C1) / 32));
+    gn_finalize_kernel<<<(n_pg + 127) / 128, 128, 0, s>>>(partial, S, n_pg, inv_n, (double)eps, stats);
+    return wdm_launch_status();
+}
+
+size_t gn_stats_bytes(int P) { return (((size_t)P * 64 * 4 + 255) & ~(size_t)255) + gn_partial_bytes(P); }
+
+int launch_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtype, int P, int HW, const float* stats,
+                    const float* gamma, const float* beta, int silu, void* out, cudaStream_t s) {
+    GnGeom g;
+    if (!gn_geom(C0, C1, &g)) return WDM_ERR_BAD_SHAPE;
+    const int ppi = g.threads / g.nvec;
+    // ~8 pixels per thread-row per CTA
+    int pix_per_cta = ppi * 8;
+    if (pix_per_cta > HW) pix_per_cta = HW;
+    dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, P);
+#define WDM_GN_APPLY(T, V, SILU, PREC)                                                                            \
+    gn_apply_kernel<T, V, SILU, PREC><<<grid, g.threads, 0, s>>>(reinterpret_cast<const T*>(src0), C0,             \
+                                                                 reinterpret_cast<const T*>(src1), C1, HW,         \
+                                                                 pix_per_cta, stats, gamma, beta,                  \
+                                                                 reinterpret_cast<T*>(out))
+    if (dtype == DT_F32) {
+        if (g.V == 4) { if (silu) WDM_GN_APPLY(float, 4, true, true); else WDM_GN_APPLY(float, 4, false, true); }
+        else          { if (silu) WDM_GN_APPLY(float, 8, true, true); else WDM_GN_APPLY(float, 8, false, true); }
+    } else {
+        if (g.V == 4) { if (silu) WDM_GN_APPLY(__nv_bfloat16, 4, true, false); else WDM_GN_APPLY(__nv_bfloat16, 4, false, false); }
+        else          { if (silu) WDM_GN_APPLY(__nv_bfloat16, 8, true, false); else WDM_GN_APPLY(__nv_bfloat16, 8, false, false); }
+    }
+#undef WDM_GN_APPLY
+    return wdm_launch_status();
+}
+
+int launch_upsample2x(const void* src, int dtype, int P, int H, int W, int C, void* out, cudaStream_t s) {
+    const int per16 = dtype == DT_F32 ? 4 : 8;
+    if (C % per16) return WDM_ERR_BAD_SHAPE;
+    const int C8 = C / per16;
+    const long long total = (long long)P * 4 * H * W * C8;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (dtype == DT_F32)
+        upsample2x_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(src), P, H, W, C8,
+                                                       reinterpret_cast<float*>(out));
+    else
+        upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), P, H, W, C8,
+                                                               reinterpret_cast<__nv_bfloat16*>(out));
+    return wdm_launch_status();
+}
+
+int launch_softmax_rows(const float* S, int rows, int L, void* out, int out_dtype, cudaStream_t s) {
+    if (L % 32 || L > 1024) return WDM_ERR_BAD_SHAPE;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (out_dtype == DT_F32)
+        softmax_rows_kernel<float><<<grid, 256, 0, s>>>(S, rows, L, reinterpret_cast<float*>(out));
+    else
+        softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(S, rows, L, reinterpret_cast<__nv_bfloat16*>(out));
+    return wdm_launch_status();
+}
+
+int launch_temb(const TembParams& p, cudaStream_t s) {
+    const int tc = 4 * p.ch;
+    float* h1 = p.scratch;                        // silu(dense0(emb(t)))     [T][tc]
+    float* h2 = p.scratch + (long long)p.T * tc;  // silu(dense1(h1))         [T][tc]
+    auto grid = [&](long long warps) { return (unsigned)((warps + 7) / 8); };
+    int st;
+    linear_kernel<<<grid((long long)p.T * tc), 256, 0, s>>>(nullptr, p.t, p.freqs, p.ch / 2, p.w0, p.b0, p.T, tc, p.ch,
+                                                           1, h1);
+    if ((st = wdm_launch_status()) != WDM_OK) return st;
+    linear_kernel<<<grid((long long)p.T * tc), 256, 0, s>>>(h1, nullptr, nullptr, 0, p.w1, p.b1, p.T, tc, tc, 1, h2);
+    if ((st = wdm_launch_status()) != WDM_OK) return st;
+    linear_kernel<<<grid((long long)p.T * p.total), 256, 0, s>>>(h2, nullptr, nullptr, 0, p.wp, p.bp, p.T, p.total, tc,
+                                                                0, p.out);
+    return wdm_launch_status();
+}
+
+int launch_gather_patches(const GatherParams& p, cudaStream_t s) {
+    if (p.P <= 0) return WDM_OK;
+    if (p.nsrc < 1 || p.nsrc > 3) return WDM_ERR_BAD_ARG;
+    const size_t smem = (size_t)p.Cpad * (p.R + 1) * sizeof(float);
+    if (smem > 96 * 1024) return WDM_ERR_BAD_SHAPE;
+    dim3 grid(p.R, p.P);
+    if (p.out_dtype == DT_F32) {
+        cudaFuncSetAttribute(gather_patches_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        gather_patches_kernel<float><<<grid, 256, smem, s>>>(p);
+    } else {
+        cudaFuncSetAttribute(gather_patches_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             96 * 1024);
+        gather_patches_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(p);
+    }
+    return wdm_launch_status();
+}
+
+int launch_ddim_step(const DdimParams& p, cudaStream_t s) {
+    const long long total = (long long)p.B * p.Cp * p.h * p.w;
+    if (total <= 0) return WDM_OK;
+    ddim_step_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p);
+    return wdm_launch_status();
+}
+
+int launch_pack_conv_weight(const float* w, int Cout, int Cin, int taps, int Cin_pad, void* out, int out_dtype,
+                            long long ldk, long long k_off, cudaStream_t s) {
+    const long long total = (long long)Cout * taps * Cin_pad;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (out_dtype == DT_F32)
+        pack_conv_weight_kernel<float><<<grid, 256, 0, s>>>(w, Cout, Cin, taps, Cin_pad, reinterpret_cast<float*>(out),
+                                                           ldk, k_off);
+    else
+        pack_conv_weight_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(w, Cout, Cin, taps, Cin_pad,
+                                                                   reinterpret_cast<__nv_bfloat16*>(out), ldk, k_off);
+    return wdm_launch_status();
+}
+
+}  // namespace wdm

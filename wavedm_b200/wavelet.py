@@ -58,6 +58,8 @@ def dwt4x4(x: torch.Tensor, pre_2xm1: bool = False, impl: int = _lib.WDM_WT_IMPL
     if H % 4 or W % 4:
         raise ValueError(f"H and W must be multiples of 4, got {H}x{W}")
     y = torch.empty((n, 48, H // 4, W // 4), dtype=torch.float32, device=x.device)
+    if y.numel() == 0:
+        return y
     flags = (_lib.WDM_DWT_PRE_2XM1 if pre_2xm1 else 0) | impl
     with torch.cuda.device(x.device):
         st = _lib.load().wdm_dwt4x4_fwd(x.data_ptr(), y.data_ptr(), n, H, W, flags, _lib.current_stream_ptr(x.device))
@@ -70,6 +72,8 @@ def iwt4x4(y: torch.Tensor, post_clamp: bool = False, impl: int = _lib.WDM_WT_IM
     y = _check_input(y, 48)
     n, _, h, w = y.shape
     x = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=y.device)
+    if x.numel() == 0:
+        return x
     flags = (_lib.WDM_IWT_POST_CLAMP if post_clamp else 0) | impl
     with torch.cuda.device(y.device):
         st = _lib.load().wdm_iwt4x4_fwd(y.data_ptr(), x.data_ptr(), n, h, w, flags, _lib.current_stream_ptr(y.device))
