@@ -46,6 +46,8 @@ typedef enum wdm_status {
 WDM_API int wdm_version(void);               /* 100*major + minor */
 WDM_API const char* wdm_build_arch(void);    /* "sm_100a" */
 WDM_API const char* wdm_status_string(int status);
+/* number of CUDA kernels this library has launched in this process (bench.py's "gpu_launches") */
+WDM_API long long wdm_launch_counter(void);
 
 /* ------------------------------------------------------------------------------------------------
  * 2-level Haar-packet ("c2", scale=2) wavelet transform.
@@ -122,6 +124,13 @@ WDM_API size_t wdm_unet_workspace_bytes(const wdm_unet_t* net, int P);
  * eps_out: [P, out_ch, R, R] fp32 NCHW. */
 WDM_API int wdm_unet_forward(wdm_unet_t* net, const void* x, const float* t, int T, int P, float* eps_out,
                              void* workspace, size_t workspace_bytes, void* stream);
+/* Per-kernel-class timing of the contraction (conv / GEMM) launches for the roofline report: while enabled,
+ * wdm_unet_forward brackets every contraction launch with CUDA events on the launch stream.
+ * wdm_unet_profile_read synchronises those events, returns the totals since the last read and resets:
+ *   tc_*   : tcgen05 tensor-core kernel launches;  simt_* : CUDA-core kernel launches. */
+WDM_API int wdm_unet_profile_enable(wdm_unet_t* net, int on);
+WDM_API int wdm_unet_profile_read(wdm_unet_t* net, double* tc_ms, double* tc_flops, long long* tc_launches,
+                                  double* simt_ms, double* simt_flops, long long* simt_launches);
 
 /* ------------------------------------------------------------------------------------------------
  * Sampler kernels.

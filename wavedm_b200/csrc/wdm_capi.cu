@@ -19,3 +19,8 @@ extern "C" const char* wdm_status_string(int status) {
     if (status <= WDM_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(WDM_ERR_CUDA_BASE - status));
     return "unknown status";
 }
+
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+extern "C" long long wdm_launch_counter_add(long long n) { return g_launches.fetch_add(n) + n; }
+extern "C" long long wdm_launch_counter(void) { return g_launches.load(); }

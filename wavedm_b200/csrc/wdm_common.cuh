@@ -15,7 +15,10 @@
 // CUDA errors are passed through as WDM_ERR_CUDA_BASE - cudaError (always < WDM_ERR_CUDA_BASE).
 static inline int wdm_cuda_error(int e) { return WDM_ERR_CUDA_BASE - e; }
 
+// every kernel launcher ends with wdm_launch_status(): it also feeds the launch counter (wdm_launch_counter)
+extern "C" long long wdm_launch_counter_add(long long n);
 static inline int wdm_launch_status() {
+    wdm_launch_counter_add(1);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
         cudaGetLastError();

@@ -262,6 +262,20 @@ struct wdm_unet {
     size_t packed_bytes = 0;
     // packed small tensors
     float *w0 = nullptr, *b0 = nullptr, *w1 = nullptr, *b1 = nullptr, *wp = nullptr, *bp = nullptr, *freqs = nullptr;
+    // profiling (wdm_unet_profile_*)
+    bool profile = false;
+    struct Span {
+        cudaEvent_t a, b;
+        double flops;
+        bool tc;
+    };
+    std::vector<Span> spans;
+    ~wdm_unet() {
+        for (auto& s : spans) {
+            cudaEventDestroy(s.a);
+            cudaEventDestroy(s.b);
+        }
+    }
 };
 
 namespace wdm {
@@ -408,10 +422,20 @@ void free_act(Ctx& c, Act& a) {
 int run_gemm(Ctx& c, const GemmParams& p) {
     if (c.dry() || c.st != WDM_OK) return c.st;
     int st;
-    if (c.net->dt == DT_BF16 && !(c.net->flags & WDM_ENGINE_NO_TC) && gemm_tc_supported(p))
-        st = launch_gemm_tc(p, c.s);
-    else
-        st = launch_gemm_simt(p, c.s);
+    const bool tc = c.net->dt == DT_BF16 && !(c.net->flags & WDM_ENGINE_NO_TC) && gemm_tc_supported(p);
+    wdm_unet::Span sp;
+    if (c.net->profile) {
+        cudaEventCreate(&sp.a);
+        cudaEventCreate(&sp.b);
+        sp.flops = 2.0 * p.M * p.N * p.K;
+        sp.tc = tc;
+        cudaEventRecord(sp.a, c.s);
+    }
+    st = tc ? launch_gemm_tc(p, c.s) : launch_gemm_simt(p, c.s);
+    if (c.net->profile) {
+        cudaEventRecord(sp.b, c.s);
+        c.net->spans.push_back(sp);
+    }
     c.fail(st);
     return st;
 }
@@ -701,6 +725,37 @@ extern "C" int wdm_unet_forward(wdm_unet_t* net, const void* x, const float* t, 
     ar.base = reinterpret_cast<char*>(workspace);
     ar.cap = workspace_bytes;
     return forward_impl(net, &ar, x, t, T, P, eps_out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int wdm_unet_profile_enable(wdm_unet_t* net, int on) {
+    if (!net) return WDM_ERR_BAD_ARG;
+    net->profile = on != 0;
+    return WDM_OK;
+}
+
+extern "C" int wdm_unet_profile_read(wdm_unet_t* net, double* tc_ms, double* tc_flops, long long* tc_launches,
+                                     double* simt_ms, double* simt_flops, long long* simt_launches) {
+    if (!net) return WDM_ERR_BAD_ARG;
+    double ms[2] = {0, 0}, fl[2] = {0, 0};
+    long long n[2] = {0, 0};
+    for (auto& s : net->spans) {
+        cudaError_t e = cudaEventSynchronize(s.b);
+        if (e != cudaSuccess) return wdm_cuda_error((int)e);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, s.a, s.b);
+        const int k = s.tc ? 0 : 1;
+        ms[k] += t, fl[k] += s.flops, n[k] += 1;
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    net->spans.clear();
+    if (tc_ms) *tc_ms = ms[0];
+    if (tc_flops) *tc_flops = fl[0];
+    if (tc_launches) *tc_launches = n[0];
+    if (simt_ms) *simt_ms = ms[1];
+    if (simt_flops) *simt_flops = fl[1];
+    if (simt_launches) *simt_launches = n[1];
+    return WDM_OK;
 }
 
 extern "C" int wdm_gather_patches(const float* src0, int C0, const float* src1, int C1, const float* src2, int C2,

@@ -210,3 +210,16 @@ class UNetEngine:
                                         xt.data_ptr(), x0_out.data_ptr(), xt_next.data_ptr(), ctypes.c_float(at),
                                         ctypes.c_float(at_next), _lib.current_stream_ptr(self.device))
         _lib.check(st, "wdm_ddim_step")
+
+    # ------------------------------------------------------------------------------------------ profiling
+    def profile(self, on: bool) -> None:
+        _lib.check(self.lib.wdm_unet_profile_enable(self.handle, 1 if on else 0), "wdm_unet_profile_enable")
+
+    def profile_read(self):
+        """(tc_ms, tc_flops, tc_launches, simt_ms, simt_flops, simt_launches) since the last read."""
+        d = [ctypes.c_double() for _ in range(4)]
+        n = [ctypes.c_longlong() for _ in range(2)]
+        st = self.lib.wdm_unet_profile_read(self.handle, ctypes.byref(d[0]), ctypes.byref(d[1]), ctypes.byref(n[0]),
+                                            ctypes.byref(d[2]), ctypes.byref(d[3]), ctypes.byref(n[1]))
+        _lib.check(st, "wdm_unet_profile_read")
+        return d[0].value, d[1].value, n[0].value, d[2].value, d[3].value, n[1].value

@@ -1,0 +1,159 @@
+"""DiffusiveRestoration -- drop-in for the reference's ``models/restoration.py:16-196`` (the eval driver).
+
+``restore`` keeps the reference's loader contract ``(x[B,6,H,W] in [0,1], id, total)``, its pick of
+``x0_preds[-5]`` (restoration.py:108), its four output variants, PSNR prints and PNG side effects.
+The DWT -> sample -> IWT sandwich runs on the sm_100a kernels: ``data_transform`` is fused into the DWT
+load and ``inverse_data_transform`` into the IWT store (bit-identical to the separate elementwise ops).
+``restore_batch`` is the same computation without file I/O for a whole batch (what bench.py times).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import logging as wlogging
+from . import metrics
+from .wavelet import dwt4x4, iwt4x4
+
+
+def data_transform(X):
+    return 2 * X - 1.0
+
+
+def inverse_data_transform(X):
+    return torch.clamp((X + 1.0) / 2.0, 0.0, 1.0)
+
+
+class DiffusiveRestoration:
+    def __init__(self, diffusion, args, config):
+        super(DiffusiveRestoration, self).__init__()
+        self.args = args
+        self.config = config
+        self.diffusion = diffusion
+        if os.path.isfile(args.resume):
+            self.diffusion.model.eval()
+        else:
+            print('Pre-trained diffusion model path is missing!')
+        d = config.data
+        if getattr(d, "lap", False) or getattr(d, "global_attn", False) or getattr(d, "wavelet_in_unet", False) \
+                or not getattr(d, "wavelet", True) or d.dataset == "DPD_Dual":
+            raise NotImplementedError("only the raindrop_wavelet.yml mode (wavelet=True, wavelet_in_unet=False, "
+                                      "lap=False, global_attn=False) is implemented (SURVEY.md 2.1 / 8f-4)")
+
+    # ------------------------------------------------------------------------------------------ core
+    @torch.no_grad()
+    def restore_batch(self, x: torch.Tensor, r: Optional[int] = None, noise: Optional[torch.Tensor] = None,
+                      x_other: Optional[torch.Tensor] = None, want_variants: bool = False) -> Dict[str, torch.Tensor]:
+        """restoration.py:73-135 for a batch ``x`` [B,6,H,W] in [0,1] (cond || gt), without prints / files.
+        ``noise`` overrides the initial ``randn`` (restoration.py:177) so CPU-oracle runs can be reproduced;
+        ``x_other`` overrides the HFRM branch (restoration.py:94-102). Returns device tensors."""
+        df, cfgm = self.diffusion, self.config.model
+        dev = df.device
+        x = x.flatten(start_dim=0, end_dim=1) if x.ndim == 5 else x
+        x = x.to(dev, torch.float32)
+        cond01 = x[:, :3].contiguous()
+        x_cond = dwt4x4(cond01, pre_2xm1=True)            # DWT(data_transform(cond))
+        x_gt = dwt4x4(x[:, 3:].contiguous(), pre_2xm1=True)
+        wd, wd_wav = None, None
+        use_other = bool(cfgm.use_other_channels)
+        if cfgm.pred_channels < cfgm.in_channels and x_other is None:
+            wd = df.generator(cond01)
+            wd_wav = dwt4x4(wd.contiguous(), pre_2xm1=True)
+        if use_other and x_other is None:
+            x_other = wd_wav[:, cfgm.other_channels_begin:].contiguous()
+        hf = wd_wav[:, cfgm.pred_channels:] if wd_wav is not None else x_other
+        p_size = self.config.data.image_size
+        h_list, w_list = self.overlapping_grid_indices(x_cond, output_size=p_size, r=r)
+        corners = [(i, j) for i in h_list for j in w_list]
+        if noise is None:
+            noise = torch.randn((x_cond.shape[0], cfgm.pred_channels, x_cond.shape[2], x_cond.shape[3]), device=dev)
+        skip = self.config.diffusion.num_diffusion_timesteps // self.args.sampling_timesteps
+        seq = range(0, self.config.diffusion.num_diffusion_timesteps, skip)
+        net = df.model.module if hasattr(df.model, "module") else df.model
+        from .sampler import DdimSampler
+        sampler = DdimSampler(net.engine(), max_patches=getattr(self.args, "max_patches", None))
+        xs_hist, x0_hist = sampler.sample(noise, x_cond, x_other if use_other else None, seq, df.betas, corners, p_size)
+        latent = x0_hist[-5]                                # restoration.py:108
+        out: Dict[str, torch.Tensor] = {"latent": latent, "x_cond_wav": x_cond, "x_gt_wav": x_gt}
+        lat = latent[:, :cfgm.pred_channels]
+        if cfgm.pred_channels < cfgm.in_channels:
+            out["output"] = iwt4x4(torch.cat([lat, hf], dim=1), post_clamp=True)
+            if want_variants:
+                out["lrdiff_hrgt"] = iwt4x4(torch.cat([lat, x_gt[:, cfgm.pred_channels:]], dim=1), post_clamp=True)
+                out["lrgt_hrwdnet"] = iwt4x4(torch.cat([x_gt[:, :cfgm.pred_channels], hf], dim=1), post_clamp=True)
+                out["lrgt_hrcond"] = iwt4x4(torch.cat([x_gt[:, :cfgm.pred_channels], x_cond[:, cfgm.pred_channels:]], dim=1),
+                                            post_clamp=True)
+        else:
+            out["output"] = iwt4x4(latent.contiguous(), post_clamp=True)
+        if want_variants:
+            out["cond"] = iwt4x4(x_cond, post_clamp=True)
+            if wd is not None:
+                out["all_wdnet"] = wd
+        return out
+
+    # ------------------------------------------------------------------------------------------ reference API
+    def restore(self, val_loader, validation='snow', r=None):
+        """restoration.py:63-168."""
+        image_folder = os.path.join(self.args.image_folder, self.config.data.dataset, validation)
+        cfgm = self.config.model
+        psnr_torch, psnr_np, psnr_gpu, psnr_wdnet = [], [], [], []
+        with torch.no_grad():
+            for i, (x, y, total) in enumerate(val_loader):
+                print(f"starting processing from image {y}")
+                x = x.flatten(start_dim=0, end_dim=1) if x.ndim == 5 else x
+                res = self.restore_batch(x, r=r, want_variants=True)
+                x_output, x_cond = res["output"], res["cond"]
+                gt = x[:, 3:, :, :]
+                p1 = metrics.torchPSNR(gt, x_output.cpu())
+                pc = metrics.torchPSNR(gt, x_cond.cpu())
+                p_gpu = metrics.calculate_psnr_in_GPU(gt.to(x_output.device), x_output, True)
+
+                def u8(t):
+                    return torch.clamp(t[0] * 255, 0, 255).cpu().numpy().transpose((1, 2, 0))
+                p_np = metrics.calculate_psnr(u8(gt), u8(x_output), True)
+                if "all_wdnet" in res:
+                    psnr_wdnet.append(metrics.calculate_psnr(u8(gt), u8(res["all_wdnet"]), True))
+                psnr_torch.append(p1)
+                psnr_np.append(p_np)
+                psnr_gpu.append(p_gpu)
+                print("psnr this", p1)
+                print("psnr cond", pc)
+                if cfgm.use_other_channels and cfgm.pred_channels < cfgm.in_channels:
+                    wlogging.save_image(res["lrgt_hrwdnet"], os.path.join(image_folder, f"{y}_lrgt_hrwdnet.png"))
+                    wlogging.save_image(res["all_wdnet"], os.path.join(image_folder, f"{y}_all_wdnet.png"))
+                    wlogging.save_image(res["lrgt_hrcond"], os.path.join(image_folder, f"{y}_lrgt_hrcond.png"))
+                    wlogging.save_image(res["lrdiff_hrgt"], os.path.join(image_folder, f"{y}_lrdiff_hrgt.png"))
+                wlogging.save_image(x_output, os.path.join(image_folder, f"{y}_output.png"))
+                wlogging.save_image(x_cond, os.path.join(image_folder, f"{y}_cond.png"))
+                wlogging.save_image(gt, os.path.join(image_folder, f"{y}_gt.png"))
+        print("psnr all torch", np.mean(psnr_torch))
+        print("psnr all np", np.mean(psnr_np))
+        print("psnr all GPU", np.mean(psnr_gpu))
+        if psnr_wdnet:
+            print("psnr all wdnet", np.mean(psnr_wdnet))
+
+    def diffusive_restoration(self, x_cond, x_other=None, r=None, last=True, total=None, use_global=False,
+                              use_other=False):
+        """restoration.py:170-185."""
+        p_size = self.config.data.patch_size if self.config.data.wavelet_in_unet else self.config.data.image_size
+        h_list, w_list = self.overlapping_grid_indices(x_cond, output_size=p_size, r=r)
+        corners = [(i, j) for i in h_list for j in w_list]
+        x = torch.randn((x_cond.shape[0], self.config.model.pred_channels, x_cond.shape[2], x_cond.shape[3]),
+                        device=self.diffusion.device)
+        return self.diffusion.sample_image(x_cond, x, x_other=x_other, last=last, patch_locs=corners,
+                                           patch_size=p_size, total=total, use_global=use_global, use_other=use_other)
+
+    def overlapping_grid_indices(self, x_cond, output_size, r=None):
+        """restoration.py:187-196."""
+        _, c, h, w = x_cond.shape
+        r = 16 if r is None else r
+        h_list = [i for i in range(0, h - output_size + 1, r)]
+        w_list = [i for i in range(0, w - output_size + 1, r)]
+        if h_list[-1] + output_size < h:
+            h_list.append(h - output_size)
+        if w_list[-1] + output_size < w:
+            w_list.append(w - output_size)
+        return h_list, w_list

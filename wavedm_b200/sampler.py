@@ -1,0 +1,97 @@
+"""Batched DDIM (eta = 0) overlapping-patch sampler on the CUDA engine.
+
+This is the device-side restatement of ``models/ddm_wavelet.py:437-506`` (and of the whole-image twin
+``utils/sampling.py:23-44``): per timestep ONE gather kernel per patch chunk (crop + concat + NHWC),
+the UNet engine, and ONE fused scatter-average + DDIM-update kernel; ``xs`` / ``x0_preds`` stay on the
+device and are copied out once at the end (the reference does two D2H copies and four ``.item()`` syncs
+per step). The reference's sampler is batch-1 only (it writes ``et_output[0]``, ddm_wavelet.py:486); here
+every image of the batch is an independent reference run.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from .engine import UNetEngine
+
+
+def alpha_table(betas: torch.Tensor) -> torch.Tensor:
+    """``compute_alpha`` (utils/sampling.py:10-13) for every t in [-1, T): float32 cumprod in the same
+    (sequential, CPU) order; entry [t+1] is alpha_bar_t and entry [0] = 1."""
+    b = betas.detach().to("cpu", torch.float32)
+    return (1 - torch.cat([torch.zeros(1), b], dim=0)).cumprod(dim=0)
+
+
+def make_patch_table(n_images: int, corners: Sequence[Tuple[int, int]], device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """[(image, hi, wi)] sorted by image with the reference's corner order inside an image, + ranges."""
+    rows = [(b, int(hi), int(wi)) for b in range(n_images) for (hi, wi) in corners]
+    patches = torch.tensor(rows, dtype=torch.int32).reshape(-1, 3).to(device)
+    first = (torch.arange(n_images + 1, dtype=torch.int32) * len(corners)).to(device)
+    return patches, first
+
+
+class DdimSampler:
+    def __init__(self, engine: UNetEngine, max_patches: Optional[int] = None):
+        self.engine = engine
+        self.max_patches = int(max_patches or engine.max_patches)
+
+    @torch.no_grad()
+    def sample(self, x: torch.Tensor, x_cond: torch.Tensor, x_other: Optional[torch.Tensor], seq: Sequence[int],
+               betas: torch.Tensor, corners: Sequence[Tuple[int, int]], p_size: int, eta: float = 0.0,
+               keep_history: bool = True):
+        """Returns (xs_hist [S, B, C, h, w], x0_hist [S, B, C, h, w]) device tensors (history of x_{t-1} and
+        of the x0 predictions, in sampling order). With keep_history=False only the last entries are kept
+        ([1, B, C, h, w])."""
+        eng = self.engine
+        if eta != 0.0:
+            raise NotImplementedError("only eta = 0 (deterministic DDIM) is implemented; the reference never "
+                                      "passes another value (ddm_wavelet.py:302)")
+        if p_size != eng.R:
+            raise ValueError(f"patch size {p_size} != UNet resolution {eng.R}")
+        dev = eng.device
+        x = x.to(dev, torch.float32).contiguous()
+        x_cond = x_cond.to(dev, torch.float32).contiguous()
+        srcs_tail = []
+        if x_other is not None:
+            srcs_tail = [x_other.to(dev, torch.float32).contiguous()]
+        B, Cp, h, w = x.shape
+        if x_cond.shape[1] + Cp + (srcs_tail[0].shape[1] if srcs_tail else 0) != eng.in_channels:
+            raise ValueError("x_cond / x / x_other channel counts do not add up to the UNet's input channels")
+        seq = list(seq)
+        seq_next = [-1] + seq[:-1]
+        S = len(seq)
+        alphas = alpha_table(betas)
+        patches, first = make_patch_table(B, corners, dev)
+        P = patches.shape[0]
+        tvals = torch.tensor(list(reversed(seq)), dtype=torch.float32).to(dev)
+        nh = S if keep_history else 1
+        xs_hist = torch.empty((nh, B, Cp, h, w), dtype=torch.float32, device=dev)
+        x0_hist = torch.empty((nh, B, Cp, h, w), dtype=torch.float32, device=dev)
+        eps = torch.empty((P, eng.out_ch, eng.R, eng.R), dtype=torch.float32, device=dev)
+        chunk = min(self.max_patches, P)
+        xin = torch.empty((chunk, eng.R, eng.R, eng.cin_pad), dtype=eng.dtype, device=dev)
+        xt = x
+        for k, (i_t, j_t) in enumerate(zip(reversed(seq), reversed(seq_next))):
+            at = float(alphas[i_t + 1])
+            at_next = float(alphas[j_t + 1])
+            t = tvals[k:k + 1]
+            for p0 in range(0, P, chunk):
+                n = min(chunk, P - p0)
+                eng.gather([x_cond, xt] + srcs_tail, patches[p0:p0 + n], out=xin[:n])
+                eng.forward_nhwc(xin[:n], t, out=eps[p0:p0 + n])
+            slot = k if keep_history else 0
+            eng.ddim_step(eps, patches, first, xt, x0_hist[slot], xs_hist[slot], at, at_next)
+            xt = xs_hist[slot]
+        return xs_hist, x0_hist
+
+    @torch.no_grad()
+    def sample_lists(self, x, x_cond, x_other, seq, betas, corners, p_size, eta=0.0):
+        """Reference return contract (ddm_wavelet.py:449,498,503,506): ``xs`` = [x] + S CPU tensors,
+        ``x0_preds`` = S CPU tensors."""
+        xs_hist, x0_hist = self.sample(x, x_cond, x_other, seq, betas, corners, p_size, eta=eta)
+        xs_cpu = xs_hist.to("cpu")
+        x0_cpu = x0_hist.to("cpu")
+        xs: List[torch.Tensor] = [x] + [xs_cpu[i] for i in range(xs_cpu.shape[0])]
+        x0_preds: List[torch.Tensor] = [x0_cpu[i] for i in range(x0_cpu.shape[0])]
+        return xs, x0_preds
