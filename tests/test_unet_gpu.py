@@ -123,6 +123,45 @@ def test_gemm_simt_fp32_conv_cases(case):
     assert (outb - ref).abs().max().item() <= 4e-2 * max(1.0, ref.abs().max().item())
 
 
+TC_CASES = [
+    # P, C0, C1, Cout, H, k, stride, ups, temb_rows, residual
+    (2, 128, 0, 128, 16, 3, 1, 0, 0, False),    # BN=128, 2 rows of 64.. (16x16: 8 rows per tile)
+    (3, 128, 0, 256, 16, 3, 1, 0, 1, True),     # BN=256, broadcast temb, residual, M = 768 (6 tiles)
+    (2, 128, 128, 256, 8, 3, 1, 0, 2, True),    # concat (two tensor maps), per-patch temb, 8x8 -> 2 patches per tile
+    (4, 256, 128, 128, 8, 1, 1, 0, 0, True),    # 1x1 over a concat
+    (2, 128, 0, 128, 16, 3, 2, 0, 0, False),    # stride-2 via TMA element strides (out 8x8)
+    (2, 128, 0, 128, 64, 3, 2, 0, 0, False),    # stride-2 64 -> 32
+    (1, 64, 0, 64, 64, 3, 1, 0, 0, False),      # BN=64, 64-wide rows
+    (3, 192, 0, 768, 8, 3, 1, 0, 0, False),     # odd patch count: M = 192 -> partial last tile (8x8)
+    (2, 1536, 0, 768, 8, 3, 1, 0, 1, True),     # deepest level shape, K = 13824
+    (1, 128, 0, 128, 32, 1, 1, 0, 0, False),    # 1x1, 32-wide rows
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_gemm_tc_conv_cases(case):
+    """tcgen05 implicit-GEMM vs torch fp32 conv on the SAME bf16-rounded inputs (differences: accumulation order
+    and the bf16 rounding of the stored output, 2^-9 relative)."""
+    P, C0, C1, Cout, H, k, stride, ups, trows, has_res = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    rb = lambda t: t.bfloat16().float()
+    x = rb(torch.randn(P, C0, H, H, generator=g))
+    x2 = rb(torch.randn(P, C1, H, H, generator=g)) if C1 else None
+    w = rb(torch.randn(Cout, C0 + C1, k, k, generator=g) / (k * (C0 + C1) ** 0.5))
+    bias = torch.randn(Cout, generator=g)
+    temb = torch.randn(trows, Cout, generator=g) if trows else None
+    Ho = H // 2 if stride == 2 else H
+    res = rb(torch.randn(P, Cout, Ho, Ho, generator=g)) if has_res else None
+    ref = ref_conv(x, x2, w, bias, stride, ups, temb, res)
+    out = run_conv(x, x2, w, bias, stride, ups, temb, res, 1, _lib.WDM_GEMM_IMPL_TC)
+    scale = max(1.0, ref.abs().max().item())
+    err = (out - ref).abs().max().item()
+    assert err <= 6e-3 * scale, (err, scale)
+    # and it agrees with the CUDA-core kernel on the same data
+    outs = run_conv(x, x2, w, bias, stride, ups, temb, res, 1, _lib.WDM_GEMM_IMPL_SIMT)
+    assert (out - outs).abs().max().item() <= 1e-2 * scale
+
+
 @pytest.mark.parametrize("dtype", [0, 1])
 @pytest.mark.parametrize("shape", [(3, 128, 0, 64), (2, 256, 128, 16), (2, 768, 768, 64), (1, 1280, 0, 256), (2, 512, 0, 256)])
 def test_groupnorm_silu(dtype, shape):
@@ -192,6 +231,41 @@ def test_unet_small_bf16_simt_vs_oracle():
     ref = torch.from_numpy(g["out"])
     rel = ((out - ref).norm() / ref.norm()).item()
     assert rel <= 3e-2, rel
+
+
+def test_unet_small_bf16_tc_vs_oracle():
+    g = golden("unet_small.npz")
+    cfg = small_cfg()
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    eng = _engine(cfg, sd, "bf16")
+    x, t = torch.from_numpy(g["x"]), torch.from_numpy(g["t"])
+    out = eng.forward(x.to(DEV), t.to(DEV)).cpu()
+    ref = torch.from_numpy(g["out"])
+    rel = ((out - ref).norm() / ref.norm()).item()
+    assert rel <= 3e-2, rel
+    eng.profile(True)
+    eng.forward(x.to(DEV), t.to(DEV))
+    tc_ms, tc_fl, tc_n, s_ms, s_fl, s_n = eng.profile_read()
+    eng.profile(False)
+    assert tc_n > 0, "the bf16 engine did not launch the tcgen05 kernel"
+
+
+def test_unet_full_bf16_tc_vs_reference_golden():
+    g = golden("unet_full.npz")
+    cfg = O.default_config()
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    eng = _engine(cfg, sd, "bf16")
+    gen = torch.Generator().manual_seed(int(g["x_seed"]))
+    x = torch.randn(2, 96, 64, 64, generator=gen)
+    out = eng.forward(x.to(DEV), torch.from_numpy(g["t"]).to(DEV)).cpu()
+    ref = torch.from_numpy(g["out"])
+    rel = ((out - ref).norm() / ref.norm()).item()
+    assert rel <= 3e-2, rel
+    eng.profile(True)
+    eng.forward(x.to(DEV), torch.from_numpy(g["t"]).to(DEV))
+    tc_ms, tc_fl, tc_n, s_ms, s_fl, s_n = eng.profile_read()
+    eng.profile(False)
+    assert tc_n >= 100 and tc_fl > 0.95 * (tc_fl + s_fl), (tc_n, s_n, tc_fl, s_fl)
 
 
 def test_unet_full_fp32_vs_reference_golden():

@@ -1,9 +1,400 @@
-// wdm_gemm_tc.cu -- tcgen05 / TMA implicit-GEMM (bf16 in, fp32 accumulate in TMEM). Placeholder until the
-// kernel lands: reports every shape as unsupported so the executor uses the CUDA-core path.
+// wdm_gemm_tc.cu -- the tensor-core contraction kernel: TMA-fed tcgen05.mma implicit GEMM for sm_100a.
+//
+//   out[m][n] = alpha * sum_k A[m][k] * B[n][k]  (+ bias[n] + temb[patch(m)][n] + residual[m][n])
+//
+// A (activations, NHWC bf16) is never materialised as an im2col matrix: for every (tap, 64-channel chunk) the
+// producer issues ONE 4-D TMA box load {64 ch, Wb, Hb, Nb} at the tap-shifted pixel coordinates; out-of-image
+// pixels are zero-filled by the TMA unit (that is the conv padding), stride-2 convs use the tensor map's element
+// strides, and a channel concat is two tensor maps. The box lands in shared memory as 128 pixel rows x 128 bytes
+// with the 128-byte swizzle, which is exactly the canonical K-major UMMA operand layout. B (packed weights
+// [Cout][taps*Cin], or a per-patch K matrix for attention) comes in through a 2-D / 3-D map the same way.
+//
+// One persistent CTA per SM, 8 warps, warp-specialised:
+//   warp 0     TMA producer          (STAGES-deep smem ring, full/empty mbarriers)
+//   warp 1     MMA issuer            (one elected lane; tcgen05.mma kind::f16 M=128 N=BN K=16, fp32 accum in TMEM)
+//   warp 2     TMEM allocator
+//   warps 4-7  epilogue              (tcgen05.ld 32 lanes x 32 columns -> bias/temb/residual -> bf16/fp32 global)
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the mainloop
+// of tile i+1.
 #include "wdm_common.cuh"
 #include "wdm_engine.h"
+#include "wdm_ptx.cuh"
+#include "wdm_tmap.h"
 
 namespace wdm {
-bool gemm_tc_supported(const GemmParams&) { return false; }
-int launch_gemm_tc(const GemmParams&, cudaStream_t) { return WDM_ERR_UNSUPPORTED; }
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;                       // bf16 elements per k-block = 128 bytes = one swizzle span
+constexpr int kABytes = kBM * kBK * 2;        // 16 KiB
+constexpr int kSmemBudget = 196608;           // operand ring bytes (192 KiB)
+constexpr int kThreads = 256;
+
+struct TcArgs {
+    int m_tiles, n_tiles;
+    int M;
+    int kc0, kc1;            // 64-channel chunks per tap taken from source 0 / 1
+    int taps, stride, pad;
+    int Wout, HWout;         // output width, pixels per patch
+    int b_batched, tiles_per_batch;
+    float alpha;
+    const float* bias;
+    const float* temb;
+    int temb_rows, temb_ld;
+    const void* residual;
+    int ldr;
+    void* out;
+    int ldo;
+    int out_f32;
+};
+
+// K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) /*LBO (ignored for swizzled K-major)*/ |
+           (64ull << 32) /*SBO = 1024 B*/ | (1ull << 46) /*version*/ | (2ull << 61) /*SWIZZLE_128B*/;
+}
+// cute::UMMA::InstrDescriptor: c=F32, a=b=BF16, K-major both, N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+    static constexpr int kBBytes = BN * kBK * 2;
+    static constexpr int kStage = kABytes + kBBytes;
+    static constexpr int kStages = kSmemBudget / kStage;
+    static constexpr int kTmemCols = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
+    static constexpr int kSmem = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStage);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + C::kStages;
+    uint64_t* tfull = bars + 2 * C::kStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA0);
+        ptx::prefetch_tmap(&tmA1);
+        ptx::prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull[s], 1);
+            ptx::mbar_init(&tempty[s], 128);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = a.m_tiles * a.n_tiles;
+    const int kc_per_tap = a.kc0 + a.kc1;
+    const int kblocks = a.taps * kc_per_tap;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+            const int m0 = mt * kBM;
+            const int n_img = m0 / a.HWout;
+            const int oh0 = (m0 - n_img * a.HWout) / a.Wout;
+            const int bb = a.b_batched ? mt / a.tiles_per_batch : 0;
+            for (int tap = 0; tap < a.taps; ++tap) {
+                const int dy = a.taps == 9 ? tap / 3 : 0, dx = a.taps == 9 ? tap % 3 : 0;
+                const int cx = dx - a.pad, cy = oh0 * a.stride + dy - a.pad;
+                for (int kc = 0; kc < kc_per_tap; ++kc, ++it) {
+                    const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
+                    ptx::mbar_wait(&empty[s], ph ^ 1);
+                    if (lane == 0) {
+                        uint8_t* sa = smem + s * C::kStage;
+                        uint8_t* sb = sa + kABytes;
+                        ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
+                        if (kc < a.kc0)
+                            ptx::tma_load_4d(sa, &tmA0, &full[s], kc * kBK, cx, cy, n_img);
+                        else
+                            ptx::tma_load_4d(sa, &tmA1, &full[s], (kc - a.kc0) * kBK, cx, cy, n_img);
+                        const int kcoord = (tap * kc_per_tap + kc) * kBK;
+                        if (a.b_batched)
+                            ptx::tma_load_3d(sb, &tmB, &full[s], kcoord, nt * BN, bb);
+                        else
+                            ptx::tma_load_2d(sb, &tmB, &full[s], kcoord, nt * BN);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = make_idesc(kBM, BN);
+        uint32_t it = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+            ptx::mbar_wait(&tempty[as], aph ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
+                ptx::mbar_wait(&full[s], ph);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = ptx::smem_u32(smem + s * C::kStage);
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k)
+                        ptx::umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    ptx::umma_commit(&empty[s]);
+                    if (kb == kblocks - 1) ptx::umma_commit(&tfull[as]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        uint32_t tl = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+            const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+            ptx::mbar_wait(&tfull[as], aph);
+            ptx::tc_fence_after();
+            const long long m = (long long)mt * kBM + row;
+            const bool valid = m < a.M;
+            const float* temb_row = nullptr;
+            if (a.temb) temb_row = a.temb + (a.temb_rows > 1 ? (long long)(m / a.HWout) * a.temb_ld : 0);
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + ch * 32, r);
+                ptx::tmem_ld_wait();
+                if (valid) {
+                    const int n = nt * BN + ch * 32;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * a.alpha;
+                    if (a.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n + j));
+                            v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+                        }
+                    }
+                    if (temb_row) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(temb_row + n + j));
+                            v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+                        }
+                    }
+                    if (a.out_f32) {
+                        if (a.residual) {
+                            const float* rp = reinterpret_cast<const float*>(a.residual) + m * a.ldr + n;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(rp + j);
+                                v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+                            }
+                        }
+                        float* op = reinterpret_cast<float*>(a.out) + m * a.ldo + n;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+                        if (a.residual) {
+                            const uint4* rp =
+                                reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.residual) + m * a.ldr + n);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 u = rp[q];
+                                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    v[q * 8 + 2 * i] += __uint_as_float(w[i] << 16);
+                                    v[q * 8 + 2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+                                }
+                            }
+                        }
+                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + m * a.ldo + n);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                __nv_bfloat162 t = __floats2bfloat162_rn(v[q * 8 + 2 * i], v[q * 8 + 2 * i + 1]);
+                                w[i] = *reinterpret_cast<uint32_t*>(&t);
+                            }
+                            op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty[as]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct Geom {
+    int Wb, Hb, Nb;  // output-space box: Wb * Hb * Nb == 128
+};
+
+bool tile_geom(int Hout, int Wout, Geom* g) {
+    if (Wout <= 0 || Wout > 128 || (128 % Wout)) return false;
+    const int rows = 128 / Wout;  // tile rows of the output image
+    const int HW = Hout * Wout;
+    if (HW >= 128) {
+        if (Hout % rows) return false;
+        g->Wb = Wout, g->Hb = rows, g->Nb = 1;
+    } else {
+        if (128 % HW) return false;
+        g->Wb = Wout, g->Hb = Hout, g->Nb = 128 / HW;
+    }
+    return true;
+}
+
+int pick_bn(int N) {
+    if (N % 256 == 0) return 256;
+    if (N % 128 == 0) return 128;
+    if (N % 64 == 0) return 64;
+    return 0;
+}
+
+int num_sms_tc() {
+    static int sms = []() {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        return v;
+    }();
+    return sms;
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& B, const TcArgs& a, cudaStream_t s) {
+    using C = Cfg<BN>;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    if (e != cudaSuccess) return wdm_cuda_error((int)e);
+    const int tiles = a.m_tiles * a.n_tiles;
+    const int grid = tiles < num_sms_tc() ? tiles : num_sms_tc();
+    gemm_tc_kernel<BN><<<grid, kThreads, C::kSmem, s>>>(A0, A1, B, a);
+    return wdm_launch_status();
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const GemmParams& p) {
+    if (p.a_dtype != DT_BF16 || p.b_dtype != DT_BF16) return false;
+    if (p.out_dtype != DT_BF16 && p.out_dtype != DT_F32) return false;
+    if (p.b_layout != BL_NK || p.ups) return false;
+    if ((p.C0 % kBK) || (p.C1 % kBK) || p.C0 <= 0) return false;
+    if (p.taps != 1 && p.taps != 9) return false;
+    if (p.stride != 1 && p.stride != 2) return false;
+    if (p.taps == 1 && p.stride != 1) return false;
+    if (!pick_bn(p.N)) return false;
+    Geom g;
+    if (!tile_geom(p.Hout, p.Wout, &g)) return false;
+    if (p.stride == 2 && (2 * g.Wb > 256 || 2 * g.Hb > 256)) return false;
+    if (p.b_batch_stride) {
+        if ((p.Hout * p.Wout) % kBM) return false;
+        if (p.b_batch_stride % 8) return false;
+    }
+    if ((p.ld0 % 8) || (p.C1 && (p.ld1 % 8)) || (p.ldb % 8) || (p.ldo % 8) || (p.residual && (p.ldr % 8))) return false;
+    if (!wdm_aligned(p.src0, 16) || (p.C1 && !wdm_aligned(p.src1, 16)) || !wdm_aligned(p.B, 16) ||
+        !wdm_aligned(p.out, 16) || (p.residual && !wdm_aligned(p.residual, 16)))
+        return false;
+    if (p.bias && !wdm_aligned(p.bias, 16)) return false;
+    if (p.temb && (!wdm_aligned(p.temb, 16) || (p.temb_ld % 4))) return false;
+    if (p.K != p.taps * (p.C0 + p.C1)) return false;
+    return true;
+}
+
+int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
+    if (!gemm_tc_supported(p)) return WDM_ERR_UNSUPPORTED;
+    if (p.M <= 0) return WDM_OK;
+    Geom g;
+    tile_geom(p.Hout, p.Wout, &g);
+    const int HWout = p.Hout * p.Wout;
+    const int npatch = (p.M + HWout - 1) / HWout;
+    const int BN = pick_bn(p.N);
+
+    CUtensorMap A0, A1, B;
+    auto make_a = [&](CUtensorMap* m, const void* src, int C, int ld) -> int {
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)npatch};
+        uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)p.Win * ld * 2, (uint64_t)p.Hin * p.Win * ld * 2};
+        uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(g.Wb * p.stride), (uint32_t)(g.Hb * p.stride), (uint32_t)g.Nb};
+        uint32_t es[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
+        return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, src, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, es);
+    };
+    int r = make_a(&A0, p.src0, p.C0, p.ld0);
+    if (r) return r < 0 ? WDM_ERR_UNSUPPORTED : wdm_cuda_error(r);
+    if (p.C1) {
+        r = make_a(&A1, p.src1, p.C1, p.ld1);
+        if (r) return r < 0 ? WDM_ERR_UNSUPPORTED : wdm_cuda_error(r);
+    } else {
+        A1 = A0;
+    }
+    if (p.b_batch_stride) {
+        const int nb = p.M / HWout;
+        uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.N, (uint64_t)nb};
+        uint64_t strides[2] = {(uint64_t)p.ldb * 2, (uint64_t)p.b_batch_stride * 2};
+        uint32_t box[3] = {(uint32_t)kBK, (uint32_t)BN, 1};
+        r = make_tmap(&B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.B, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+        uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+        uint64_t strides[1] = {(uint64_t)p.ldb * 2};
+        uint32_t box[2] = {(uint32_t)kBK, (uint32_t)BN};
+        r = make_tmap(&B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.B, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    }
+    if (r) return r < 0 ? WDM_ERR_UNSUPPORTED : wdm_cuda_error(r);
+
+    TcArgs a;
+    a.m_tiles = (p.M + kBM - 1) / kBM;
+    a.n_tiles = p.N / BN;
+    a.M = p.M;
+    a.kc0 = p.C0 / kBK, a.kc1 = p.C1 / kBK;
+    a.taps = p.taps, a.stride = p.stride, a.pad = p.pad;
+    a.Wout = p.Wout, a.HWout = HWout;
+    a.b_batched = p.b_batch_stride ? 1 : 0;
+    a.tiles_per_batch = p.b_batch_stride ? HWout / kBM : 0;
+    a.alpha = p.alpha;
+    a.bias = p.bias, a.temb = p.temb, a.temb_rows = p.temb_rows, a.temb_ld = p.temb_ld;
+    a.residual = p.residual, a.ldr = p.ldr, a.out = p.out, a.ldo = p.ldo;
+    a.out_f32 = p.out_dtype == DT_F32;
+    switch (BN) {
+        case 256: return launch_bn<256>(A0, A1, B, a, s);
+        case 128: return launch_bn<128>(A0, A1, B, a, s);
+        default: return launch_bn<64>(A0, A1, B, a, s);
+    }
+}
+
 }  // namespace wdm

@@ -36,10 +36,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded spin: a protocol bug traps (-> CUDA error surfaced to the caller) instead of hanging the GPU.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
+        if (++spins > 4096u) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0)
+                t0 = now;
+            else if (now - t0 > 4000000000ull)  // 4 s: a broken pipeline protocol must not hang the GPU
+                __trap();
+        }
     }
 }
 

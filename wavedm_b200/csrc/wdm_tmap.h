@@ -28,7 +28,8 @@ inline PFN_tmapEncodeTiled tmap_encode_fn() {
 // Returns 0 on success, a CUresult (>0) on failure, -1 if the entry point is unavailable.
 inline int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz,
-                     CUtensorMapL2promotion l2 = CU_TENSOR_MAP_L2_PROMOTION_L2_128B) {
+                     CUtensorMapL2promotion l2 = CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     const uint32_t* elem_strides = nullptr) {
     PFN_tmapEncodeTiled fn = tmap_encode_fn();
     if (!fn) return -1;
     cuuint64_t d[5], s[4];
@@ -36,7 +37,7 @@ inline int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const v
     for (int i = 0; i < rank; ++i) {
         d[i] = dims[i];
         b[i] = box[i];
-        e[i] = 1;
+        e[i] = elem_strides ? elem_strides[i] : 1;
         if (i + 1 < rank) s[i] = strides_bytes[i];
     }
     CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
