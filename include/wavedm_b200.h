@@ -167,6 +167,12 @@ typedef struct wdm_gemm_params {
     int ldr;
     void* out;
     int ldo, a_dtype, b_dtype, out_dtype;
+    /* optional GroupNorm side-car (tensor-core path only): per (32-row group, 4-column block) partial sums of the
+     * values written to `out`: stats_out[M/32][N/4][2] = (sum, sum of squares), fp32. NULL = not produced. */
+    float* stats_out;
+    /* != 0: the A operand is ONE matrix shared by every batch (rows m % (Hout*Wout)); used with a per-batch B to
+     * compute V^T = Wv * h^T for attention. */
+    int a_shared;
 } wdm_gemm_params;
 #define WDM_GEMM_IMPL_SIMT 0
 #define WDM_GEMM_IMPL_TC 1

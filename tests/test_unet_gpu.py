@@ -27,10 +27,10 @@ class GemmParams(ctypes.Structure):
         [(n, ctypes.c_int) for n in ("ldb", "b_layout", "M", "N", "K")] + \
         [("alpha", ctypes.c_float), ("bias", ctypes.c_void_p), ("temb", ctypes.c_void_p), ("temb_rows", ctypes.c_int),
          ("temb_ld", ctypes.c_int), ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int), ("out", ctypes.c_void_p)] + \
-        [(n, ctypes.c_int) for n in ("ldo", "a_dtype", "b_dtype", "out_dtype")]
+        [(n, ctypes.c_int) for n in ("ldo", "a_dtype", "b_dtype", "out_dtype")] + [("stats_out", ctypes.c_void_p), ("a_shared", ctypes.c_int)]
 
 
-def run_conv(x, x2, w, bias, stride, ups, temb, residual, dtype, impl):
+def run_conv(x, x2, w, bias, stride, ups, temb, residual, dtype, impl, want_stats=False):
     """x, x2: NCHW fp32 torch (cpu); w OIHW. Runs the C-ABI gemm on NHWC tensors, returns NCHW fp32."""
     lib = _lib.load()
     td = torch.float32 if dtype == 0 else torch.bfloat16
@@ -67,10 +67,15 @@ def run_conv(x, x2, w, bias, stride, ups, temb, residual, dtype, impl):
         p.residual, p.ldr = r.data_ptr(), Cout
     p.out, p.ldo = out.data_ptr(), Cout
     p.a_dtype = p.b_dtype = p.out_dtype = dtype
+    stats = None
+    if want_stats:
+        stats = torch.full((p.M // 32, Cout // 4, 2), float("nan"), device=DEV)
+        p.stats_out = stats.data_ptr()
     st = lib.wdm_gemm(ctypes.byref(p), impl, torch.cuda.current_stream().cuda_stream)
     _lib.check(st, "wdm_gemm")
     torch.cuda.synchronize()
-    return out.float().permute(0, 3, 1, 2).cpu()
+    res = out.float().permute(0, 3, 1, 2).cpu()
+    return (res, stats.cpu()) if want_stats else res
 
 
 def ref_conv(x, x2, w, bias, stride, ups, temb, residual):
@@ -160,6 +165,27 @@ def test_gemm_tc_conv_cases(case):
     # and it agrees with the CUDA-core kernel on the same data
     outs = run_conv(x, x2, w, bias, stride, ups, temb, res, 1, _lib.WDM_GEMM_IMPL_SIMT)
     assert (out - outs).abs().max().item() <= 1e-2 * scale
+
+
+@pytest.mark.parametrize("case", [(2, 128, 0, 256, 16, 3, 1, 0, 1, True), (4, 128, 0, 768, 8, 1, 1, 0, 0, False),
+                                  (1, 128, 0, 128, 64, 3, 1, 0, 0, False)])
+def test_gemm_tc_groupnorm_sidecar(case):
+    """The tensor-core epilogue's GroupNorm side-car = per (32-row group, 4-channel block) sums of the stored tensor."""
+    P, C0, C1, Cout, H, k, stride, ups, trows, has_res = case
+    g = torch.Generator().manual_seed(17)
+    rb = lambda t: t.bfloat16().float()
+    x = rb(torch.randn(P, C0, H, H, generator=g))
+    w = rb(torch.randn(Cout, C0, k, k, generator=g) / (k * C0 ** 0.5))
+    bias = torch.randn(Cout, generator=g)
+    temb = torch.randn(trows, Cout, generator=g) if trows else None
+    res = rb(torch.randn(P, Cout, H, H, generator=g)) if has_res else None
+    ref = ref_conv(x, None, w, bias, stride, ups, temb, res)          # [P, Cout, H, W] fp32 (pre-rounding values)
+    out, stats = run_conv(x, None, w, bias, stride, ups, temb, res, 1, _lib.WDM_GEMM_IMPL_TC, want_stats=True)
+    rows = ref.permute(0, 2, 3, 1).reshape(-1, Cout)                   # [M, Cout]
+    blk = rows.reshape(rows.shape[0] // 32, 32, Cout // 4, 4)
+    s_ref = torch.stack([blk.sum(dim=(1, 3)), (blk ** 2).sum(dim=(1, 3))], dim=-1)
+    assert not torch.isnan(stats).any()
+    assert (stats - s_ref).abs().max().item() <= 2e-3 * max(1.0, s_ref.abs().max().item())
 
 
 @pytest.mark.parametrize("dtype", [0, 1])

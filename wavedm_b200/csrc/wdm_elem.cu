@@ -143,11 +143,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
     const int C = C0 + C1, nvec = C / V, cpg = C / 32;
     const int p = blockIdx.y;
     const int vec = threadIdx.x % nvec, lane_pix = threadIdx.x / nvec, ppi = blockDim.x / nvec;
-    const int c = vec * V, g = c / cpg;
-    const float mean = stats[(p * 32 + g) * 2], rstd = stats[(p * 32 + g) * 2 + 1];
+    const int c = vec * V;
     float a[V], b[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
+        const int g = (c + i) / cpg;  // a vector may straddle a group boundary: per-element statistics
+        const float mean = stats[(p * 32 + g) * 2], rstd = stats[(p * 32 + g) * 2 + 1];
         a[i] = rstd * gamma[c + i];
         b[i] = beta[c + i] - mean * a[i];
     }
@@ -161,22 +162,71 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
     T* o = out + (long long)p * HW * C + c;
     const int px0 = blockIdx.x * pix_per_cta;
     const int px1 = min(HW, px0 + pix_per_cta);
-    for (int px = px0 + lane_pix; px < px1; px += ppi) {
-        float v[V];
-        Vec<T, V>::load(base + (long long)px * ld, v);
+    constexpr int U = 4;  // independent 16-byte loads in flight per thread
+    for (int px = px0 + lane_pix; px < px1; px += U * ppi) {
+        float v[U][V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-            float y = fmaf(v[i], a[i], b[i]);
-            if (kSilu) y = kPrecise ? silu_precise(y) : wdm_silu(y);
-            v[i] = y;
-        }
-        Vec<T, V>::store(o + (long long)px * C, v);
+        for (int u = 0; u < U; ++u)
+            if (px + u * ppi < px1) Vec<T, V>::load(base + (long long)(px + u * ppi) * ld, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (px + u * ppi < px1) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    float y = fmaf(v[u][i], a[i], b[i]);
+                    if (kSilu) y = kPrecise ? silu_precise(y) : wdm_silu(y);
+                    v[u][i] = y;
+                }
+                Vec<T, V>::store(o + (long long)(px + u * ppi) * C, v[u]);
+            }
+    }
+}
+
+// (mean, rstd) per (patch, group) from the side-car partial sums the tensor-core epilogue wrote next to the
+// tensor(s): sc[M/32][C/4][2]. One warp per (patch, group); double accumulation.
+__global__ void __launch_bounds__(256) gn_finalize_sidecar_kernel(const float* __restrict__ sc0, int C0,
+                                                                  const float* __restrict__ sc1, int C1, int HW,
+                                                                  int P, double eps, float* __restrict__ stats) {
+    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= P * 32) return;
+    const int lane = threadIdx.x & 31;
+    const int p = wid >> 5, g = wid & 31;
+    const int cpg = (C0 + C1) / 32, nb = cpg >> 2, fb = (g * cpg) >> 2, nrg = HW >> 5;
+    const int b0n = C0 >> 2, b1n = C1 >> 2;
+    double sum = 0, sq = 0;
+    for (int it = lane; it < nrg * nb; it += 32) {
+        const int rgi = it / nb, b = fb + (it - rgi * nb);
+        const float2 t = b < b0n
+            ? *reinterpret_cast<const float2*>(sc0 + (((long long)p * nrg + rgi) * b0n + b) * 2)
+            : *reinterpret_cast<const float2*>(sc1 + (((long long)p * nrg + rgi) * b1n + (b - b0n)) * 2);
+        sum += t.x, sq += t.y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) {
+        const double inv_n = 1.0 / ((double)HW * cpg);
+        const double mean = sum * inv_n;
+        double var = sq * inv_n - mean * mean;
+        if (var < 0) var = 0;
+        stats[2 * wid] = (float)mean;
+        stats[2 * wid + 1] = (float)(1.0 / sqrt(var + eps));
     }
 }
 
 struct GnGeom {
     int V, nvec, threads;
 };
+inline bool gn_geom_apply(int C0, int C1, GnGeom* g) {
+    const int C = C0 + C1;
+    if ((C % 32) || ((C / 32) % 4) || (C0 % 8) || (C % 8) || C / 8 > 256) return false;
+    g->V = 8;
+    g->nvec = C / 8;
+    g->threads = (256 / g->nvec) * g->nvec;
+    return true;
+}
 inline bool gn_geom(int C0, int C1, GnGeom* g) {
     const int C = C0 + C1;
     if (C % 32) return false;
@@ -420,25 +470,30 @@ size_t gn_stats_bytes(int P) { return (((size_t)P * 64 * 4 + 255) & ~(size_t)255
 int launch_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtype, int P, int HW, const float* stats,
                     const float* gamma, const float* beta, int silu, void* out, cudaStream_t s) {
     GnGeom g;
-    if (!gn_geom(C0, C1, &g)) return WDM_ERR_BAD_SHAPE;
+    if (!gn_geom_apply(C0, C1, &g)) return WDM_ERR_BAD_SHAPE;
     const int ppi = g.threads / g.nvec;
-    // ~8 pixels per thread-row per CTA
-    int pix_per_cta = ppi * 8;
+    int pix_per_cta = ppi * 16;
     if (pix_per_cta > HW) pix_per_cta = HW;
     dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, P);
-#define WDM_GN_APPLY(T, V, SILU, PREC)                                                                            \
-    gn_apply_kernel<T, V, SILU, PREC><<<grid, g.threads, 0, s>>>(reinterpret_cast<const T*>(src0), C0,             \
+#define WDM_GN_APPLY(T, SILU, PREC)                                                                               \
+    gn_apply_kernel<T, 8, SILU, PREC><<<grid, g.threads, 0, s>>>(reinterpret_cast<const T*>(src0), C0,             \
                                                                  reinterpret_cast<const T*>(src1), C1, HW,         \
                                                                  pix_per_cta, stats, gamma, beta,                  \
                                                                  reinterpret_cast<T*>(out))
     if (dtype == DT_F32) {
-        if (g.V == 4) { if (silu) WDM_GN_APPLY(float, 4, true, true); else WDM_GN_APPLY(float, 4, false, true); }
-        else          { if (silu) WDM_GN_APPLY(float, 8, true, true); else WDM_GN_APPLY(float, 8, false, true); }
+        if (silu) WDM_GN_APPLY(float, true, true); else WDM_GN_APPLY(float, false, true);
     } else {
-        if (g.V == 4) { if (silu) WDM_GN_APPLY(__nv_bfloat16, 4, true, false); else WDM_GN_APPLY(__nv_bfloat16, 4, false, false); }
-        else          { if (silu) WDM_GN_APPLY(__nv_bfloat16, 8, true, false); else WDM_GN_APPLY(__nv_bfloat16, 8, false, false); }
+        if (silu) WDM_GN_APPLY(__nv_bfloat16, true, false); else WDM_GN_APPLY(__nv_bfloat16, false, false);
     }
 #undef WDM_GN_APPLY
+    return wdm_launch_status();
+}
+
+int launch_gn_finalize_sidecar(const float* sc0, int C0, const float* sc1, int C1, int P, int HW, float eps,
+                               float* stats, cudaStream_t s) {
+    if (((C0 + C1) % 128) || (C0 % 4) || (C1 % 4) || (HW % 32) || !sc0 || (C1 && !sc1)) return WDM_ERR_BAD_SHAPE;
+    const int warps = P * 32;
+    gn_finalize_sidecar_kernel<<<(warps + 7) / 8, 256, 0, s>>>(sc0, C0, sc1, C1, HW, P, (double)eps, stats);
     return wdm_launch_status();
 }
 

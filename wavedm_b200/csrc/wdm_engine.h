@@ -38,6 +38,10 @@ int launch_conv_small_cout(const void* src, int dtype, int P, int H, int W, int 
 // GroupNorm(32 groups, eps) statistics over up to two concatenated NHWC sources -> stats[P][32][2] = (mean, rstd)
 int launch_gn_stats(const void* src0, int C0, const void* src1, int C1, int dtype, int P, int HW, float eps,
                     float* stats, cudaStream_t stream);
+// same result from the side-car partial sums written by the tensor-core epilogue (wdm_gemm_params::stats_out) of the
+// kernel(s) that produced the source tensor(s): sc[P*HW/32][C/4][2]
+int launch_gn_finalize_sidecar(const float* sc0, int C0, const float* sc1, int C1, int P, int HW, float eps,
+                               float* stats, cudaStream_t stream);
 size_t gn_stats_bytes(int P);  // size of the `stats` scratch buffer (mean/rstd + double partial sums)
 // y = ((x - mean) * rstd * gamma + beta), optionally * sigmoid(.)  -> out [P, HW, C0+C1] (materialises the concat)
 int launch_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtype, int P, int HW, const float* stats,

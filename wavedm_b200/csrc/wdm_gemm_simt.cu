@@ -56,6 +56,21 @@ __device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&v)[4]) {
     v[2] = __uint_as_float(q.y << 16), v[3] = __uint_as_float(q.y & 0xffff0000u);
 }
 
+// plain (non-__ldg) 8-element loads, safe for shared memory
+__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+__device__ __forceinline__ void lds8(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
 template <typename TA, typename TB, typename TO, int kBLayout>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
     __shared__ __align__(16) float As[2][BK][PITCH];
@@ -75,7 +90,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
     const int lr = tid & 127, kh = tid >> 7;
     const bool a_row_ok = (tile_row0 + lr) < group_rows;
     const long long am = m_base + lr;
-    const int ab = a_row_ok ? (int)(am / rows_per_batch) : 0;
+    const int ab = (a_row_ok && !p.a_shared) ? (int)(am / rows_per_batch) : 0;
     const int ar = a_row_ok ? (int)(am % rows_per_batch) : 0;
     const int aoy = ar / p.Wout, aox = ar % p.Wout;
     const int Ct = p.C0 + p.C1;
@@ -230,53 +245,83 @@ int launch_t(const GemmParams& p, cudaStream_t s) {
 }
 
 // ---- conv_out: Cout <= 4, NHWC in, NCHW fp32 out -------------------------------------------------------
+// One CTA per (patch, output row): the three input rows are staged in shared memory once (coalesced 16-byte loads,
+// zero rows/columns for the padding), weights [Cout][9][C] in shared memory as fp32. Thread = (4 adjacent pixels,
+// one 8-channel slice); the C/8 slices of a pixel group sit in adjacent lanes and are shuffle-reduced.
 template <typename T>
-__global__ void __launch_bounds__(128) conv_small_cout_kernel(const T* __restrict__ src, int P, int H, int W, int C,
+__global__ void __launch_bounds__(256) conv_small_cout_kernel(const T* __restrict__ src, int P, int H, int W, int C,
                                                               const float* __restrict__ w,
                                                               const float* __restrict__ bias, int Cout,
                                                               float* __restrict__ out) {
-    extern __shared__ float sw[];  // [Cout][9][C]
+    extern __shared__ __align__(16) unsigned char smem_cs[];
+    const int y = blockIdx.x, p = blockIdx.y;
+    const int Wp = W + 2;
+    T* rows = reinterpret_cast<T*>(smem_cs);                                    // [3][W+2][C]
+    float* sw = reinterpret_cast<float*>(smem_cs + (size_t)3 * Wp * C * sizeof(T));  // [Cout][9][C]
     for (int i = threadIdx.x; i < Cout * 9 * C; i += blockDim.x) sw[i] = w[i];
+    constexpr int VE = 16 / sizeof(T);  // elements per 16-byte vector
+    const int vec_per_row = Wp * C / VE;
+    for (int i = threadIdx.x; i < 3 * vec_per_row; i += blockDim.x) {
+        const int r = i / vec_per_row, v = i - r * vec_per_row;
+        const int px = (v * VE) / C - 1, c = (v * VE) % C;
+        const int iy = y + r - 1;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (iy >= 0 && iy < H && px >= 0 && px < W)
+            q = __ldg(reinterpret_cast<const uint4*>(src + (((long long)p * H + iy) * W + px) * C + c));
+        reinterpret_cast<uint4*>(rows)[i] = q;
+    }
     __syncthreads();
-    // 4 threads per pixel: each covers a quarter of the channels, then shuffle-reduce
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long pix = gid >> 2;
-    const int part = (int)(gid & 3);
-    const long long npix = (long long)P * H * W;
-    const bool live = pix < npix;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    int b = 0, y = 0, x = 0;
-    if (live) {
-        b = (int)(pix / ((long long)H * W));
-        const int r = (int)(pix % ((long long)H * W));
-        y = r / W, x = r % W;
-        const int cq = C / 4;  // C % 32 == 0
+    const int nslice = C / 8;                 // 16 for C = 128 (must divide 32)
+    const int s = threadIdx.x % nslice;
+    const int groups_per_pass = blockDim.x / nslice;
+    for (int pg = threadIdx.x / nslice; pg * 4 < W; pg += groups_per_pass) {
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) acc[a][o] = 0.f;
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-            const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
-            if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-            const T* s = src + (((long long)b * H + iy) * W + ix) * C + part * cq;
-            for (int c = 0; c < cq; c += 8) {
-                float v[8];
-                load8<T>(s + c, v);
+            const int dy = tap / 3, dx = tap % 3;
+            float wv[4][8];
 #pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    if (o < Cout) {
-                        const float* ww = sw + (o * 9 + tap) * C + part * cq + c;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[o] = fmaf(v[i], ww[i], acc[o]);
-                    }
+            for (int o = 0; o < 4; ++o) {
+                if (o < Cout) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * C + s * 8);
+                    const float4 w1 = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * C + s * 8 + 4);
+                    wv[o][0] = w0.x, wv[o][1] = w0.y, wv[o][2] = w0.z, wv[o][3] = w0.w;
+                    wv[o][4] = w1.x, wv[o][5] = w1.y, wv[o][6] = w1.z, wv[o][7] = w1.w;
                 }
             }
-        }
-    }
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-        acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
-        acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
-    }
-    if (live && part == 0) {
-        for (int o = 0; o < Cout; ++o)
-            out[(((long long)b * Cout + o) * H + y) * W + x] = acc[o] + (bias ? bias[o] : 0.f);
+            for (int a = 0; a < 4; ++a) {
+                const int px = pg * 4 + a + dx;  // index in the padded row (pixel x + dx - 1 + 1)
+                float v[8];
+                lds8(rows + ((size_t)dy * Wp + px) * C + s * 8, v);
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+                    if (o < Cout) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[a][o] = fmaf(v[i], wv[o][i], acc[a][o]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (o < Cout) {
+                    for (int off = nslice >> 1; off; off >>= 1) acc[a][o] += __shfl_xor_sync(0xffffffffu, acc[a][o], off);
+                }
+        if (s == 0) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+                if (o < Cout) {
+                    float* d = out + (((long long)p * Cout + o) * H + y) * W + pg * 4;
+                    const float b = bias ? bias[o] : 0.f;
+                    *reinterpret_cast<float4*>(d) = make_float4(acc[0][o] + b, acc[1][o] + b, acc[2][o] + b, acc[3][o] + b);
+                }
+        }
     }
 }
 
@@ -296,17 +341,22 @@ int launch_gemm_simt(const GemmParams& p, cudaStream_t s) {
 
 int launch_conv_small_cout(const void* src, int dtype, int P, int H, int W, int C, const float* w, const float* bias,
                            int Cout, float* out, cudaStream_t s) {
-    if (Cout < 1 || Cout > 4 || (C % 32)) return WDM_ERR_BAD_SHAPE;
-    const size_t smem = (size_t)Cout * 9 * C * sizeof(float);
-    if (smem > 48 * 1024) return WDM_ERR_BAD_SHAPE;
-    const long long threads = (long long)P * H * W * 4;
-    const unsigned grid = (unsigned)((threads + 127) / 128);
-    if (dtype == DT_F32)
-        conv_small_cout_kernel<float><<<grid, 128, smem, s>>>(reinterpret_cast<const float*>(src), P, H, W, C, w, bias,
+    const int nslice = C / 8;
+    if (Cout < 1 || Cout > 4 || (C % 8) || nslice > 32 || (32 % nslice) || (W % 4)) return WDM_ERR_BAD_SHAPE;
+    const size_t es = dtype == DT_F32 ? 4 : 2;
+    const size_t smem = (size_t)3 * (W + 2) * C * es + (size_t)Cout * 9 * C * sizeof(float);
+    if (smem > 200 * 1024) return WDM_ERR_BAD_SHAPE;
+    dim3 grid(H, P);
+    if (dtype == DT_F32) {
+        cudaFuncSetAttribute(conv_small_cout_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv_small_cout_kernel<float><<<grid, 256, smem, s>>>(reinterpret_cast<const float*>(src), P, H, W, C, w, bias,
                                                                Cout, out);
-    else
-        conv_small_cout_kernel<__nv_bfloat16><<<grid, 128, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), P,
+    } else {
+        cudaFuncSetAttribute(conv_small_cout_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+        conv_small_cout_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(src), P,
                                                                        H, W, C, w, bias, Cout, out);
+    }
     return wdm_launch_status();
 }
 

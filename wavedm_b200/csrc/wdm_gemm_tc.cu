@@ -36,7 +36,7 @@ struct TcArgs {
     int kc0, kc1;            // 64-channel chunks per tap taken from source 0 / 1
     int taps, stride, pad;
     int Wout, HWout;         // output width, pixels per patch
-    int b_batched, tiles_per_batch;
+    int b_batched, tiles_per_batch, a_shared;
     float alpha;
     const float* bias;
     const float* temb;
@@ -46,6 +46,8 @@ struct TcArgs {
     void* out;
     int ldo;
     int out_f32;
+    float* stats;   // GroupNorm side-car [M/32][N/4][2] or null
+    int N;
 };
 
 // K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1).
@@ -116,7 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-            const int m0 = mt * kBM;
+            const int m0 = (a.a_shared ? mt % a.tiles_per_batch : mt) * kBM;
             const int n_img = m0 / a.HWout;
             const int oh0 = (m0 - n_img * a.HWout) / a.Wout;
             const int bb = a.b_batched ? mt / a.tiles_per_batch : 0;
@@ -247,6 +249,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             op[q] = make_uint4(w[0], w[1], w[2], w[3]);
                         }
                     }
+                    if (a.stats) {
+                        // per 4-column block (sum, sum of squares) of this row ...
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) {
+                            const float x0 = v[4 * b], x1 = v[4 * b + 1], x2 = v[4 * b + 2], x3 = v[4 * b + 3];
+                            r[2 * b] = __float_as_uint((x0 + x1) + (x2 + x3));
+                            r[2 * b + 1] = __float_as_uint(fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3));
+                        }
+                    }
+                } else if (a.stats) {
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) r[b] = 0u;
+                }
+                if (a.stats) {
+                    // ... reduce-scattered over the warp's 32 rows: 16 values, 16 shuffles; lane 2k ends with value k
+                    float s8[8], s4[4], s2[2], s1;
+                    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float keep = __uint_as_float(h16 ? r[i + 8] : r[i]);
+                        const float send = __uint_as_float(h16 ? r[i] : r[i + 8]);
+                        s8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float keep = h8 ? s8[i + 4] : s8[i], send = h8 ? s8[i] : s8[i + 4];
+                        s4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float keep = h4 ? s4[i + 2] : s4[i], send = h4 ? s4[i] : s4[i + 2];
+                        s2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    {
+                        const float keep = h2 ? s2[1] : s2[0], send = h2 ? s2[0] : s2[1];
+                        s1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+                    const long long rg = ((long long)mt * kBM + ew * 32) >> 5;
+                    if (!(lane & 1) && (long long)mt * kBM + ew * 32 < a.M)
+                        a.stats[(rg * (a.N >> 2) + ((nt * BN + ch * 32) >> 2)) * 2 + (lane >> 1)] = s1;
                 }
             }
             ptx::tc_fence_before();
@@ -326,6 +369,7 @@ bool gemm_tc_supported(const GemmParams& p) {
         if ((p.Hout * p.Wout) % kBM) return false;
         if (p.b_batch_stride % 8) return false;
     }
+    if (p.a_shared && (!p.b_batch_stride || p.temb || p.taps != 1)) return false;
     if ((p.ld0 % 8) || (p.C1 && (p.ld1 % 8)) || (p.ldb % 8) || (p.ldo % 8) || (p.residual && (p.ldr % 8))) return false;
     if (!wdm_aligned(p.src0, 16) || (p.C1 && !wdm_aligned(p.src1, 16)) || !wdm_aligned(p.B, 16) ||
         !wdm_aligned(p.out, 16) || (p.residual && !wdm_aligned(p.residual, 16)))
@@ -342,7 +386,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     Geom g;
     tile_geom(p.Hout, p.Wout, &g);
     const int HWout = p.Hout * p.Wout;
-    const int npatch = (p.M + HWout - 1) / HWout;
+    const int npatch = p.a_shared ? 1 : (p.M + HWout - 1) / HWout;
     const int BN = pick_bn(p.N);
 
     CUtensorMap A0, A1, B;
@@ -386,10 +430,13 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     a.Wout = p.Wout, a.HWout = HWout;
     a.b_batched = p.b_batch_stride ? 1 : 0;
     a.tiles_per_batch = p.b_batch_stride ? HWout / kBM : 0;
+    a.a_shared = p.a_shared ? 1 : 0;
     a.alpha = p.alpha;
     a.bias = p.bias, a.temb = p.temb, a.temb_rows = p.temb_rows, a.temb_ld = p.temb_ld;
     a.residual = p.residual, a.ldr = p.ldr, a.out = p.out, a.ldo = p.ldo;
     a.out_f32 = p.out_dtype == DT_F32;
+    a.stats = p.stats_out;
+    a.N = p.N;
     switch (BN) {
         case 256: return launch_bn<256>(A0, A1, B, a, s);
         case 128: return launch_bn<128>(A0, A1, B, a, s);

@@ -246,6 +246,7 @@ struct Arena {
 struct Act {
     void* p = nullptr;
     int H = 0, W = 0, C = 0;
+    float* stats = nullptr;  // GroupNorm side-car [P*H*W/32][C/4][2] written by the producing tensor-core kernel
 };
 
 }  // namespace
@@ -417,12 +418,20 @@ Act new_act(Ctx& c, int H, int W, int C) {
 void free_act(Ctx& c, Act& a) {
     c.ar->free(a.p);
     a.p = nullptr;
+    if (a.stats) {
+        c.ar->free(a.stats);
+        a.stats = nullptr;
+    }
+}
+
+bool will_use_tc(const Ctx& c, const GemmParams& p) {
+    return c.net->dt == DT_BF16 && !(c.net->flags & WDM_ENGINE_NO_TC) && gemm_tc_supported(p);
 }
 
 int run_gemm(Ctx& c, const GemmParams& p) {
     if (c.dry() || c.st != WDM_OK) return c.st;
     int st;
-    const bool tc = c.net->dt == DT_BF16 && !(c.net->flags & WDM_ENGINE_NO_TC) && gemm_tc_supported(p);
+    const bool tc = will_use_tc(c, p);
     wdm_unet::Span sp;
     if (c.net->profile) {
         cudaEventCreate(&sp.a);
@@ -442,7 +451,7 @@ int run_gemm(Ctx& c, const GemmParams& p) {
 
 // conv over one or two (channel-concatenated) sources
 Act conv_op(Ctx& c, const Act& a, const Act* a2, const ConvSpec& w, int stride, int ups, const float* temb_row,
-            const Act* residual) {
+            const Act* residual, bool want_stats = false) {
     const int dt = c.net->dt;
     int Hout = a.H, Wout = a.W;
     if (ups) Hout *= 2, Wout *= 2;
@@ -462,6 +471,12 @@ Act conv_op(Ctx& c, const Act& a, const Act* a2, const ConvSpec& w, int stride, 
     p.out = o.p, p.ldo = w.Cout;
     p.a_dtype = p.b_dtype = p.out_dtype = dt;
     if (p.C0 + p.C1 != w.Cin_pad) c.fail(WDM_ERR_BAD_SHAPE);
+    if (want_stats && (p.M % 32) == 0 && (Hout * Wout) % 32 == 0 && will_use_tc(c, p)) {
+        // tensor-core epilogue also emits the GroupNorm partial sums of what it stores (no separate stats pass)
+        o.stats = reinterpret_cast<float*>(c.ar->alloc((size_t)(p.M / 32) * (p.N / 4) * 2 * sizeof(float)));
+        if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
+        p.stats_out = o.stats;
+    }
     run_gemm(c, p);
     return o;
 }
@@ -471,8 +486,12 @@ Act gn_op(Ctx& c, const Act& a, const Act* a2, const GnSpec& g, int silu) {
     Act o = new_act(c, a.H, a.W, C);
     if (C != g.C) c.fail(WDM_ERR_BAD_SHAPE);
     if (!c.dry() && c.st == WDM_OK) {
-        c.fail(launch_gn_stats(a.p, a.C, a2 ? a2->p : nullptr, a2 ? a2->C : 0, c.net->dt, c.P, a.H * a.W, kGnEps,
-                               c.gn_scratch, c.s));
+        if (a.stats && (!a2 || a2->stats))
+            c.fail(launch_gn_finalize_sidecar(a.stats, a.C, a2 ? a2->stats : nullptr, a2 ? a2->C : 0, c.P, a.H * a.W,
+                                              kGnEps, c.gn_scratch, c.s));
+        else
+            c.fail(launch_gn_stats(a.p, a.C, a2 ? a2->p : nullptr, a2 ? a2->C : 0, c.net->dt, c.P, a.H * a.W, kGnEps,
+                                   c.gn_scratch, c.s));
         if (c.st == WDM_OK)
             c.fail(launch_gn_apply(a.p, a.C, a2 ? a2->p : nullptr, a2 ? a2->C : 0, c.net->dt, c.P, a.H * a.W,
                                    c.gn_scratch, g.gamma, g.beta, silu, o.p, c.s));
@@ -483,20 +502,78 @@ Act gn_op(Ctx& c, const Act& a, const Act* a2, const GnSpec& g, int silu) {
 // models/unet.py:119-138. x2 != null: the block input is cat([x, x2], dim=1) (unet.py:379-380).
 Act resblock_op(Ctx& c, const Act& x, const Act* x2, const ResSpec& r) {
     Act n1 = gn_op(c, x, x2, r.norm1, 1);
-    Act h1 = conv_op(c, n1, nullptr, r.conv1, 1, 0, c.temb + r.temb_off, nullptr);
+    Act h1 = conv_op(c, n1, nullptr, r.conv1, 1, 0, c.temb + r.temb_off, nullptr, true);
     free_act(c, n1);
     Act n2 = gn_op(c, h1, nullptr, r.norm2, 1);
     free_act(c, h1);
     Act out;
     if (r.has_nin) {
         Act sc = conv_op(c, x, x2, r.nin, 1, 0, nullptr, nullptr);
-        out = conv_op(c, n2, nullptr, r.conv2, 1, 0, nullptr, &sc);
+        out = conv_op(c, n2, nullptr, r.conv2, 1, 0, nullptr, &sc, true);
         free_act(c, sc);
     } else {
         if (x2) c.fail(WDM_ERR_BAD_SHAPE);
-        out = conv_op(c, n2, nullptr, r.conv2, 1, 0, nullptr, &x);
+        out = conv_op(c, n2, nullptr, r.conv2, 1, 0, nullptr, &x, true);
     }
     free_act(c, n2);
+    return out;
+}
+
+// Tensor-core attention (L % 128 == 0): every contraction on the tcgen05 kernel with K-major operands only.
+//   qk  = h Wqk^T + b            [P*L][2C]
+//   vT  = Wv h^T                 [P][C][L]   (A = Wv shared by all patches, B = h per patch)  -- V transposed so that
+//   S   = (q k^T) C^-1/2         [P*L][L]     P.V has a K-major right operand; b_v is added after P.V (rows of
+//   Pm  = softmax(S)                          the softmax sum to one)
+//   O   = Pm vT^T + b_v          [P*L][C]
+//   out = O Wproj^T + b + x
+Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a) {
+    const int C = a.C, L = x.H * x.W, P = c.P;
+    const size_t es = 2;
+    Act n = gn_op(c, x, nullptr, a.norm, 0);
+    GemmParams p;
+    // qk
+    Act qk = new_act(c, x.H, x.W, 2 * C);
+    memset(&p, 0, sizeof p);
+    p.src0 = n.p, p.C0 = C, p.ld0 = C, p.Hin = p.Hout = x.H, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
+    p.B = a.qkv.pw, p.ldb = C, p.b_layout = BL_NK, p.M = P * L, p.N = 2 * C, p.K = C, p.alpha = 1.f, p.bias = a.qkv.pb;
+    p.out = qk.p, p.ldo = 2 * C, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
+    run_gemm(c, p);
+    // vT
+    void* vT = c.ar->alloc((size_t)P * C * L * es);
+    if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
+    memset(&p, 0, sizeof p);
+    p.src0 = (char*)a.qkv.pw + (size_t)2 * C * C * es, p.C0 = C, p.ld0 = C, p.a_shared = 1;
+    p.Hin = p.Hout = C / 128, p.Win = p.Wout = 128, p.taps = 1, p.stride = 1;
+    p.B = n.p, p.ldb = C, p.b_batch_stride = (long long)L * C, p.b_layout = BL_NK;
+    p.M = P * C, p.N = L, p.K = C, p.alpha = 1.f;
+    p.out = vT, p.ldo = L, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
+    run_gemm(c, p);
+    free_act(c, n);
+    // S
+    float* S = reinterpret_cast<float*>(c.ar->alloc((size_t)P * L * L * 4));
+    void* Pm = c.ar->alloc((size_t)P * L * L * es);
+    if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
+    memset(&p, 0, sizeof p);
+    p.src0 = qk.p, p.C0 = C, p.ld0 = 2 * C, p.Hin = p.Hout = x.H, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
+    p.B = (char*)qk.p + (size_t)C * es, p.b_batch_stride = (long long)L * 2 * C, p.ldb = 2 * C, p.b_layout = BL_NK;
+    p.M = P * L, p.N = L, p.K = C, p.alpha = (float)(1.0 / sqrt((double)C));
+    p.out = S, p.ldo = L, p.a_dtype = p.b_dtype = DT_BF16, p.out_dtype = DT_F32;
+    run_gemm(c, p);
+    if (!c.dry() && c.st == WDM_OK) c.fail(launch_softmax_rows(S, P * L, L, Pm, DT_BF16, c.s));
+    free_act(c, qk);
+    // O
+    Act O = new_act(c, x.H, x.W, C);
+    memset(&p, 0, sizeof p);
+    p.src0 = Pm, p.C0 = L, p.ld0 = L, p.Hin = p.Hout = x.H, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
+    p.B = vT, p.b_batch_stride = (long long)C * L, p.ldb = L, p.b_layout = BL_NK;
+    p.M = P * L, p.N = C, p.K = L, p.alpha = 1.f, p.bias = a.qkv.pb + 2 * C;
+    p.out = O.p, p.ldo = C, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
+    run_gemm(c, p);
+    c.ar->free(S);
+    c.ar->free(Pm);
+    c.ar->free(vT);
+    Act out = conv_op(c, O, nullptr, a.proj, 1, 0, nullptr, &x, true);
+    free_act(c, O);
     return out;
 }
 
@@ -504,6 +581,8 @@ Act resblock_op(Ctx& c, const Act& x, const Act* x2, const ResSpec& r) {
 Act attn_op(Ctx& c, const Act& x, const AttnSpec& a) {
     const int dt = c.net->dt;
     const int C = a.C, L = x.H * x.W, P = c.P;
+    if (dt == DT_BF16 && !(c.net->flags & WDM_ENGINE_NO_TC) && (L % 128) == 0 && (C % 128) == 0 && (L % 64) == 0)
+        return attn_op_tc(c, x, a);
     Act n = gn_op(c, x, nullptr, a.norm, 0);
     Act qkv = conv_op(c, n, nullptr, a.qkv, 1, 0, nullptr, nullptr);  // [P*L][3C]
     free_act(c, n);
@@ -538,7 +617,7 @@ Act attn_op(Ctx& c, const Act& x, const AttnSpec& a) {
     c.ar->free(S);
     c.ar->free(Pm);
     free_act(c, qkv);
-    Act out = conv_op(c, O, nullptr, a.proj, 1, 0, nullptr, &x);
+    Act out = conv_op(c, O, nullptr, a.proj, 1, 0, nullptr, &x, true);
     free_act(c, O);
     return out;
 }
@@ -564,7 +643,7 @@ int forward_impl(wdm_unet* net, Arena* ar, const void* x, const float* t, int T,
     Act xin;
     xin.p = const_cast<void*>(x), xin.H = R, xin.W = R, xin.C = net->cin_pad;
     std::vector<Act> hs;
-    hs.push_back(conv_op(c, xin, nullptr, m.conv_in, 1, 0, nullptr, nullptr));
+    hs.push_back(conv_op(c, xin, nullptr, m.conv_in, 1, 0, nullptr, nullptr, true));
     for (int lv = 0; lv < L; ++lv) {
         for (int ib = 0; ib < nrb; ++ib) {
             Act h = resblock_op(c, hs.back(), nullptr, m.down[lv].blocks[ib]);
@@ -575,7 +654,7 @@ int forward_impl(wdm_unet* net, Arena* ar, const void* x, const float* t, int T,
             }
             hs.push_back(h);
         }
-        if (m.down[lv].has_resample) hs.push_back(conv_op(c, hs.back(), nullptr, m.down[lv].resample, 2, 0, nullptr, nullptr));
+        if (m.down[lv].has_resample) hs.push_back(conv_op(c, hs.back(), nullptr, m.down[lv].resample, 2, 0, nullptr, nullptr, true));
     }
     Act h = resblock_op(c, hs.back(), nullptr, m.mid1);
     {
@@ -602,11 +681,11 @@ int forward_impl(wdm_unet* net, Arena* ar, const void* x, const float* t, int T,
         if (m.up[lv].has_resample) {
             Act h2;
             if (fold_ups) {
-                h2 = conv_op(c, h, nullptr, m.up[lv].resample, 1, 1, nullptr, nullptr);
+                h2 = conv_op(c, h, nullptr, m.up[lv].resample, 1, 1, nullptr, nullptr, true);
             } else {
                 Act u = new_act(c, h.H * 2, h.W * 2, h.C);
                 if (!c.dry() && c.st == WDM_OK) c.fail(launch_upsample2x(h.p, net->dt, P, h.H, h.W, h.C, u.p, s));
-                h2 = conv_op(c, u, nullptr, m.up[lv].resample, 1, 0, nullptr, nullptr);
+                h2 = conv_op(c, u, nullptr, m.up[lv].resample, 1, 0, nullptr, nullptr, true);
                 free_act(c, u);
             }
             free_act(c, h);
