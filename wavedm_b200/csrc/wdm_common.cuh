@@ -51,5 +51,5 @@ __device__ __forceinline__ void wdm_stg_stream(float4* p, float4 v) {
 __device__ __forceinline__ void wdm_stg_stream(float* p, float v) {
     asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-__device__ __forceinline__ float wdm_silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float wdm_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 #endif

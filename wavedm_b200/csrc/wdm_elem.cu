@@ -145,12 +145,26 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
     const int vec = threadIdx.x % nvec, lane_pix = threadIdx.x / nvec, ppi = blockDim.x / nvec;
     const int c = vec * V;
     float a[V], b[V];
+    {
+        // V = 8 channels with C/32 a multiple of 4: the vector touches at most two groups (first / last 4 channels)
+        const int g0 = c / cpg, g1 = (c + V - 1) / cpg;
+        const float2 st0 = *reinterpret_cast<const float2*>(stats + (p * 32 + g0) * 2);
+        const float2 st1 = *reinterpret_cast<const float2*>(stats + (p * 32 + g1) * 2);
+        float ga[V], be[V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-        const int g = (c + i) / cpg;  // a vector may straddle a group boundary: per-element statistics
-        const float mean = stats[(p * 32 + g) * 2], rstd = stats[(p * 32 + g) * 2 + 1];
-        a[i] = rstd * gamma[c + i];
-        b[i] = beta[c + i] - mean * a[i];
+        for (int i = 0; i < V; i += 4) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c + i));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c + i));
+            ga[i] = g4.x, ga[i + 1] = g4.y, ga[i + 2] = g4.z, ga[i + 3] = g4.w;
+            be[i] = b4.x, be[i + 1] = b4.y, be[i + 2] = b4.z, be[i + 3] = b4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const bool second = (c + i) / cpg != g0;
+            const float mean = second ? st1.x : st0.x, rstd = second ? st1.y : st0.y;
+            a[i] = rstd * ga[i];
+            b[i] = be[i] - mean * a[i];
+        }
     }
     const T* base;
     int ld, co;
@@ -472,7 +486,9 @@ int launch_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtyp
     GnGeom g;
     if (!gn_geom_apply(C0, C1, &g)) return WDM_ERR_BAD_SHAPE;
     const int ppi = g.threads / g.nvec;
-    int pix_per_cta = ppi * 16;
+    // >= ~4 CTAs per SM when the tensor allows it, but at least 8 pixels per thread-row to amortise the prologue
+    int pix_per_cta = ppi * 32;
+    while (pix_per_cta > ppi * 8 && (long long)P * ((HW + pix_per_cta - 1) / pix_per_cta) < 4 * 148) pix_per_cta >>= 1;
     if (pix_per_cta > HW) pix_per_cta = HW;
     dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, P);
 #define WDM_GN_APPLY(T, SILU, PREC)                                                                               \

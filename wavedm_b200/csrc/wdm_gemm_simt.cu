@@ -249,7 +249,7 @@ int launch_t(const GemmParams& p, cudaStream_t s) {
 // zero rows/columns for the padding), weights [Cout][9][C] in shared memory as fp32. Thread = (4 adjacent pixels,
 // one 8-channel slice); the C/8 slices of a pixel group sit in adjacent lanes and are shuffle-reduced.
 template <typename T>
-__global__ void __launch_bounds__(256) conv_small_cout_kernel(const T* __restrict__ src, int P, int H, int W, int C,
+__global__ void __launch_bounds__(256, 2) conv_small_cout_kernel(const T* __restrict__ src, int P, int H, int W, int C,
                                                               const float* __restrict__ w,
                                                               const float* __restrict__ bias, int Cout,
                                                               float* __restrict__ out) {

@@ -16,6 +16,8 @@
 //   warps 4-7  epilogue              (tcgen05.ld 32 lanes x 32 columns -> bias/temb/residual -> bf16/fp32 global)
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the mainloop
 // of tile i+1.
+#include <stdlib.h>
+
 #include "wdm_common.cuh"
 #include "wdm_engine.h"
 #include "wdm_ptx.cuh"
@@ -60,20 +62,23 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN>
+// MT = M-tiles (128 rows each) that share one B tile per k-block: MT = 2 halves the weight traffic per FLOP
+// (the kernel is L2->SM bandwidth bound) at the price of TMEM: 2 accumulators per buffer.
+template <int BN, int MT>
 struct Cfg {
     static constexpr int kBBytes = BN * kBK * 2;
-    static constexpr int kStage = kABytes + kBBytes;
+    static constexpr int kStage = MT * kABytes + kBBytes;
     static constexpr int kStages = kSmemBudget / kStage;
-    static constexpr int kTmemCols = 2 * BN;  // 512 / 256 / 128: powers of two >= 32
+    static constexpr int kBufs = (2 * MT * BN <= 512) ? 2 : 1;          // accumulator buffers in TMEM
+    static constexpr int kTmemCols = kBufs * MT * BN;                   // 512 / 256 / 128: powers of two >= 32
     static constexpr int kSmem = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStage);
@@ -109,7 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = a.m_tiles * a.n_tiles;
+    const int num_tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;  // super-tiles of MT m-tiles
     const int kc_per_tap = a.kc0 + a.kc1;
     const int kblocks = a.taps * kc_per_tap;
 
@@ -117,25 +122,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // ------------------------------------------------------------------ TMA producer
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-            const int m0 = (a.a_shared ? mt % a.tiles_per_batch : mt) * kBM;
-            const int n_img = m0 / a.HWout;
-            const int oh0 = (m0 - n_img * a.HWout) / a.Wout;
-            const int bb = a.b_batched ? mt / a.tiles_per_batch : 0;
+            const int st = tile / a.n_tiles, nt = tile - st * a.n_tiles;
+            int n_img[MT], cy0[MT];
+#pragma unroll
+            for (int h = 0; h < MT; ++h) {
+                const int mt = st * MT + h;
+                const int m0 = (a.a_shared ? mt % a.tiles_per_batch : mt) * kBM;
+                n_img[h] = m0 / a.HWout;
+                cy0[h] = ((m0 - n_img[h] * a.HWout) / a.Wout) * a.stride - a.pad;
+            }
+            const int bb = a.b_batched ? (st * MT) / a.tiles_per_batch : 0;
             for (int tap = 0; tap < a.taps; ++tap) {
                 const int dy = a.taps == 9 ? tap / 3 : 0, dx = a.taps == 9 ? tap % 3 : 0;
-                const int cx = dx - a.pad, cy = oh0 * a.stride + dy - a.pad;
+                const int cx = dx - a.pad;
                 for (int kc = 0; kc < kc_per_tap; ++kc, ++it) {
                     const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
                     ptx::mbar_wait(&empty[s], ph ^ 1);
                     if (lane == 0) {
                         uint8_t* sa = smem + s * C::kStage;
-                        uint8_t* sb = sa + kABytes;
+                        uint8_t* sb = sa + MT * kABytes;
                         ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
-                        if (kc < a.kc0)
-                            ptx::tma_load_4d(sa, &tmA0, &full[s], kc * kBK, cx, cy, n_img);
-                        else
-                            ptx::tma_load_4d(sa, &tmA1, &full[s], (kc - a.kc0) * kBK, cx, cy, n_img);
+#pragma unroll
+                        for (int h = 0; h < MT; ++h) {
+                            if (kc < a.kc0)
+                                ptx::tma_load_4d(sa + h * kABytes, &tmA0, &full[s], kc * kBK, cx, cy0[h] + dy, n_img[h]);
+                            else
+                                ptx::tma_load_4d(sa + h * kABytes, &tmA1, &full[s], (kc - a.kc0) * kBK, cx, cy0[h] + dy,
+                                                 n_img[h]);
+                        }
                         const int kcoord = (tap * kc_per_tap + kc) * kBK;
                         if (a.b_batched)
                             ptx::tma_load_3d(sb, &tmB, &full[s], kcoord, nt * BN, bb);
@@ -151,20 +165,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         constexpr uint32_t idesc = make_idesc(kBM, BN);
         uint32_t it = 0, tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-            const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+            const uint32_t as = tl % C::kBufs, aph = (tl / C::kBufs) & 1;
             ptx::mbar_wait(&tempty[as], aph ^ 1);
             ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * BN;
+            const uint32_t d_tmem = tmem_base + as * (MT * BN);
             for (int kb = 0; kb < kblocks; ++kb, ++it) {
                 const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = ptx::smem_u32(smem + s * C::kStage);
-                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
+                    const uint64_t db = make_smem_desc(sa + MT * kABytes);
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; ++k)
-                        ptx::umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < kBK / 16; ++k) {
+#pragma unroll
+                        for (int h = 0; h < MT; ++h)
+                            ptx::umma_f16_ss(d_tmem + h * BN, make_smem_desc(sa + h * kABytes) + 2 * k, db + 2 * k, idesc,
+                                             (kb | k) ? 1u : 0u);
+                    }
                     ptx::umma_commit(&empty[s]);
                     if (kb == kblocks - 1) ptx::umma_commit(&tfull[as]);
                 }
@@ -177,10 +195,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int row = ew * 32 + lane;
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-            const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-            const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+            const int st = tile / a.n_tiles, nt = tile - st * a.n_tiles;
+            const uint32_t as = tl % C::kBufs, aph = (tl / C::kBufs) & 1;
             ptx::mbar_wait(&tfull[as], aph);
             ptx::tc_fence_after();
+#pragma unroll 1
+            for (int hh = 0; hh < MT; ++hh) {
+            const int mt = st * MT + hh;
             const long long m = (long long)mt * kBM + row;
             const bool valid = m < a.M;
             const float* temb_row = nullptr;
@@ -188,7 +209,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN + ch * 32, r);
+                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (as * MT + hh) * BN + ch * 32, r);
                 ptx::tmem_ld_wait();
                 if (valid) {
                     const int n = nt * BN + ch * 32;
@@ -292,6 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         a.stats[(rg * (a.N >> 2) + ((nt * BN + ch * 32) >> 2)) * 2 + (lane >> 1)] = s1;
                 }
             }
+            }  // hh
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[as]);
         }
@@ -330,6 +352,8 @@ int pick_bn(int N) {
     return 0;
 }
 
+int g_force_mt = 0;  // testing hook (WDM_TC_FORCE_MT=1|2)
+
 int num_sms_tc() {
     static int sms = []() {
         int dev = 0, v = 0;
@@ -340,15 +364,27 @@ int num_sms_tc() {
     return sms;
 }
 
-template <int BN>
+template <int BN, int MT>
 int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& B, const TcArgs& a, cudaStream_t s) {
-    using C = Cfg<BN>;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    using C = Cfg<BN, MT>;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
-    const int tiles = a.m_tiles * a.n_tiles;
+    const int tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;
     const int grid = tiles < num_sms_tc() ? tiles : num_sms_tc();
-    gemm_tc_kernel<BN><<<grid, kThreads, C::kSmem, s>>>(A0, A1, B, a);
+    gemm_tc_kernel<BN, MT><<<grid, kThreads, C::kSmem, s>>>(A0, A1, B, a);
     return wdm_launch_status();
+}
+
+// Operand bytes a CTA pulls through L2 for the whole problem under (BN, MT): waves x bytes per k-block.
+int pick_mt(int m_tiles, int n_tiles, int BN, bool allow2) {
+    if (!allow2 || BN == 64) return 1;
+    const int sms = num_sms_tc();
+    auto cost = [&](int mt) {
+        const long long tiles = (long long)((m_tiles + mt - 1) / mt) * n_tiles;
+        const long long waves = (tiles + sms - 1) / sms;
+        return waves * (mt * kABytes + BN * kBK * 2);
+    };
+    return cost(2) < cost(1) ? 2 : 1;
 }
 
 }  // namespace
@@ -382,6 +418,13 @@ bool gemm_tc_supported(const GemmParams& p) {
 
 int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     if (!gemm_tc_supported(p)) return WDM_ERR_UNSUPPORTED;
+    {
+        static const int forced = []() {
+            const char* e = getenv("WDM_TC_FORCE_MT");
+            return e ? atoi(e) : 0;
+        }();
+        g_force_mt = forced;
+    }
     if (p.M <= 0) return WDM_OK;
     Geom g;
     tile_geom(p.Hout, p.Wout, &g);
@@ -437,11 +480,11 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     a.out_f32 = p.out_dtype == DT_F32;
     a.stats = p.stats_out;
     a.N = p.N;
-    switch (BN) {
-        case 256: return launch_bn<256>(A0, A1, B, a, s);
-        case 128: return launch_bn<128>(A0, A1, B, a, s);
-        default: return launch_bn<64>(A0, A1, B, a, s);
-    }
+    const bool allow2 = !a.b_batched || (a.tiles_per_batch % 2 == 0);
+    const int MT = g_force_mt ? (g_force_mt == 2 && allow2 && BN != 64 ? 2 : 1) : pick_mt(a.m_tiles, a.n_tiles, BN, allow2);
+    if (BN == 256) return MT == 2 ? launch_bn<256, 2>(A0, A1, B, a, s) : launch_bn<256, 1>(A0, A1, B, a, s);
+    if (BN == 128) return MT == 2 ? launch_bn<128, 2>(A0, A1, B, a, s) : launch_bn<128, 1>(A0, A1, B, a, s);
+    return launch_bn<64, 1>(A0, A1, B, a, s);
 }
 
 }  // namespace wdm
