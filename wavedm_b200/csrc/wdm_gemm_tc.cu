@@ -132,6 +132,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 cy0[h] = ((m0 - n_img[h] * a.HWout) / a.Wout) * a.stride - a.pad;
             }
             const int bb = a.b_batched ? (st * MT) / a.tiles_per_batch : 0;
+            // Weights stream from DRAM on first touch: run an L2 prefetch kPF k-blocks ahead of the smem ring so the
+            // ring's loads see L2 latency (the ring alone holds only kStages k-blocks in flight).
+            constexpr int kPF = 8;
+            if (lane == 0 && !a.b_batched) {
+                for (int j = 0; j < kPF && j < kblocks; ++j) ptx::tma_prefetch_2d(&tmB, j * kBK, nt * BN);
+            }
+            int kb_lin = 0;
             for (int tap = 0; tap < a.taps; ++tap) {
                 const int dy = a.taps == 9 ? tap / 3 : 0, dx = a.taps == 9 ? tap % 3 : 0;
                 const int cx = dx - a.pad;
@@ -141,6 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     if (lane == 0) {
                         uint8_t* sa = smem + s * C::kStage;
                         uint8_t* sb = sa + MT * kABytes;
+                        if (!a.b_batched && kb_lin + kPF < kblocks) ptx::tma_prefetch_2d(&tmB, (kb_lin + kPF) * kBK, nt * BN);
                         ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
 #pragma unroll
                         for (int h = 0; h < MT; ++h) {
@@ -157,6 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             ptx::tma_load_2d(sb, &tmB, &full[s], kcoord, nt * BN);
                     }
                     __syncwarp();
+                    ++kb_lin;
                 }
             }
         }
@@ -197,6 +206,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
             const int st = tile / a.n_tiles, nt = tile - st * a.n_tiles;
             const uint32_t as = tl % C::kBufs, aph = (tl / C::kBufs) & 1;
+            if (a.residual) {
+                // pull this thread's residual row segment(s) towards L2 while the mainloop of this tile still runs
+                const int esz = a.out_f32 ? 4 : 2;
+#pragma unroll
+                for (int hh = 0; hh < MT; ++hh) {
+                    const long long mr = (long long)(st * MT + hh) * kBM + row;
+                    if (mr < a.M) {
+                        const char* rp = reinterpret_cast<const char*>(a.residual) + (mr * a.ldr + nt * BN) * esz;
+                        for (int b = 0; b < BN * esz; b += 128)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
+                    }
+                }
+            }
             ptx::mbar_wait(&tfull[as], aph);
             ptx::tc_fence_after();
 #pragma unroll 1
@@ -206,9 +228,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const bool valid = m < a.M;
             const float* temb_row = nullptr;
             if (a.temb) temb_row = a.temb + (a.temb_rows > 1 ? (long long)(m / a.HWout) * a.temb_ld : 0);
+            const bool res16 = a.residual && !a.out_f32 && valid;
+            const uint4* res_ptr = reinterpret_cast<const uint4*>(
+                reinterpret_cast<const __nv_bfloat16*>(a.residual) + (valid ? m : 0) * a.ldr + nt * BN);
+            uint4 res_next[4];
+            if (res16) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) res_next[q] = res_ptr[q];
+            }
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 uint32_t r[32];
+                uint4 res_cur[4];
+                if (res16) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) res_cur[q] = res_next[q];
+                    if (ch + 1 < BN / 32) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) res_next[q] = res_ptr[(ch + 1) * 4 + q];
+                    }
+                }
                 ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (as * MT + hh) * BN + ch * 32, r);
                 ptx::tmem_ld_wait();
                 if (valid) {
@@ -245,11 +284,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     } else {
                         if (a.residual) {
-                            const uint4* rp =
-                                reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.residual) + m * a.ldr + n);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                const uint4 u = rp[q];
+                                const uint4 u = res_cur[q];
                                 const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
@@ -377,7 +414,7 @@ int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& B
 
 // Operand bytes a CTA pulls through L2 for the whole problem under (BN, MT): waves x bytes per k-block.
 int pick_mt(int m_tiles, int n_tiles, int BN, bool allow2) {
-    if (!allow2 || BN == 64) return 1;
+    if (!allow2 || BN != 128) return 1;  // (256, 2) has a single TMEM buffer: no epilogue overlap, measured slower
     const int sms = num_sms_tc();
     auto cost = [&](int mt) {
         const long long tiles = (long long)((m_tiles + mt - 1) / mt) * n_tiles;

@@ -102,6 +102,19 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// TMA prefetch into L2 only (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- TMA stores (smem -> global, bulk group)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
