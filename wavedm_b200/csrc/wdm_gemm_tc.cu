@@ -31,6 +31,7 @@ constexpr int kBK = 64;                       // bf16 elements per k-block = 128
 constexpr int kABytes = kBM * kBK * 2;        // 16 KiB
 constexpr int kSmemBudget = 196608;           // operand ring bytes (192 KiB)
 constexpr int kThreads = 256;
+constexpr bool kWeightPrefetch = false;  // measured: the extra L2 lookups cost more than the latency they hide
 
 struct TcArgs {
     int m_tiles, n_tiles;
@@ -135,7 +136,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             // Weights stream from DRAM on first touch: run an L2 prefetch kPF k-blocks ahead of the smem ring so the
             // ring's loads see L2 latency (the ring alone holds only kStages k-blocks in flight).
             constexpr int kPF = 8;
-            if (lane == 0 && !a.b_batched) {
+            if (kWeightPrefetch && lane == 0 && !a.b_batched) {
                 for (int j = 0; j < kPF && j < kblocks; ++j) ptx::tma_prefetch_2d(&tmB, j * kBK, nt * BN);
             }
             int kb_lin = 0;
@@ -148,7 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     if (lane == 0) {
                         uint8_t* sa = smem + s * C::kStage;
                         uint8_t* sb = sa + MT * kABytes;
-                        if (!a.b_batched && kb_lin + kPF < kblocks) ptx::tma_prefetch_2d(&tmB, (kb_lin + kPF) * kBK, nt * BN);
+                        if (kWeightPrefetch && !a.b_batched && kb_lin + kPF < kblocks) ptx::tma_prefetch_2d(&tmB, (kb_lin + kPF) * kBK, nt * BN);
                         ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
 #pragma unroll
                         for (int h = 0; h < MT; ++h) {
