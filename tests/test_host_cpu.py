@@ -1,0 +1,141 @@
+"""CPU: host-side logic of the package (no CUDA calls): patch tables, alpha table, config tree, the import shims, the
+training-path (autograd) definition of DiffusionUNet, and the N>1 path (weight broadcast + image gather) under gloo."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import REPO, golden
+from oracle import unet_oracle as O
+
+
+def small_cfg():
+    from wavedm_b200.configs import default_config
+    cfg = default_config()
+    cfg.data.image_size = 16
+    cfg.model.ch_mult = [1, 2]
+    cfg.model.num_res_blocks = 1
+    cfg.model.attn_resolutions = [8]
+    return cfg
+
+
+def small_cfg_oracle():
+    return O.default_config(data__image_size=16, model__ch=128, model__ch_mult=[1, 2], model__num_res_blocks=1,
+                            model__attn_resolutions=[8])
+
+
+def test_config_tree_matches_reference_yaml_values():
+    from wavedm_b200.configs import default_config
+    a, b = default_config(), O.default_config()
+    for sec in ("data", "model", "diffusion", "training", "sampling", "optim"):
+        assert vars(getattr(a, sec)) == vars(getattr(b, sec)), sec
+
+
+def test_patch_table_and_alpha_table():
+    from wavedm_b200.sampler import alpha_table, make_patch_table
+    g = golden("ddim_small.npz")
+    assert np.array_equal(alpha_table(torch.from_numpy(g["betas"])).numpy(), g["alphas"])
+    corners = [(0, 0), (0, 8), (8, 0)]
+    patches, first = make_patch_table(2, corners, "cpu")
+    assert patches.tolist() == [[0, 0, 0], [0, 0, 8], [0, 8, 0], [1, 0, 0], [1, 0, 8], [1, 8, 0]]
+    assert first.tolist() == [0, 3, 6] and patches.dtype == torch.int32
+
+
+def test_unet_module_matches_oracle_init_and_autograd_forward():
+    """Same seed -> same 332 tensors as the reference (via the pinned oracle); the training-path forward equals the
+    oracle's forward; inference on CPU raises (no fallback)."""
+    from wavedm_b200.unet import DiffusionUNet
+    torch.manual_seed(61)
+    net = DiffusionUNet(small_cfg())
+    sd = O.init_state_dict(small_cfg_oracle(), seed=61)
+    msd = net.state_dict()
+    assert sorted(msd) == sorted(sd) and all(torch.equal(msd[k], sd[k]) for k in sd)
+    g = golden("unet_small.npz")
+    x, t = torch.from_numpy(g["x"]), torch.from_numpy(g["t"])
+    net.train()
+    out = net(x, t)  # grad enabled + training -> differentiable PyTorch definition
+    assert out.requires_grad
+    assert (out.detach() - torch.from_numpy(g["out"])).abs().max().item() <= 2e-5
+    net.eval()
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        net(x, t)
+
+
+def test_compat_shims_import_like_the_reference_scripts():
+    sys.path.insert(0, os.path.join(REPO, "compat"))
+    try:
+        for m in ("models", "utils", "datasets"):
+            sys.modules.pop(m, None)
+        import datasets
+        import models
+        import utils
+        from models import DenoisingDiffusion, DenoisingDiffusion_Wavelet, DiffusiveRestoration  # noqa: F401
+        assert "RainDrop" in datasets.__dict__
+        for name in ("torchPSNR", "calculate_psnr", "calculate_psnr_in_GPU", "save_image", "save_checkpoint",
+                     "load_checkpoint", "get_optimizer", "compute_alpha", "generalized_steps",
+                     "generalized_steps_overlapping", "data_transform", "inverse_data_transform"):
+            assert hasattr(utils, name), name
+        assert hasattr(utils.logging, "save_checkpoint") and hasattr(utils.sampling, "compute_alpha")
+        with pytest.raises(NotImplementedError):
+            models.DenoisingDiffusion(None, None)
+    finally:
+        sys.path.remove(os.path.join(REPO, "compat"))
+        for m in ("models", "utils", "datasets"):
+            sys.modules.pop(m, None)
+
+
+def test_metrics_match_reference_formulas():
+    from wavedm_b200 import metrics
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.rand(1, 3, 16, 16, generator=g), torch.rand(1, 3, 16, 16, generator=g)
+    assert torch.equal(metrics.torchPSNR(a, b), O.torch_psnr(a, b))
+    mse = ((a - b) ** 2).mean()
+    assert abs(float(metrics.calculate_psnr_in_GPU(a, b)) - float(20 * torch.log10(1 / mse.sqrt()))) < 1e-5
+    u8 = lambda t: torch.clamp(t[0] * 255, 0, 255).numpy().transpose((1, 2, 0))
+    p = metrics.calculate_psnr(u8(a), u8(b), False)
+    assert abs(p - 20 * np.log10(255.0 / np.sqrt(np.mean((u8(a).astype(np.float64) - u8(b)) ** 2)))) < 1e-9
+
+
+def _gloo_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import contextlib
+    import io
+
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, REPO)
+    from wavedm_b200.ddm_wavelet import DenoisingDiffusion_Wavelet
+    from wavedm_b200.harness import synth_hfrm_checkpoint
+    from wavedm_b200.sampler import make_patch_table
+    cfg = small_cfg()
+    cfg.device = torch.device("cpu")
+    args = argparse.Namespace(resume="", local_rank=0, sampling_timesteps=5, grid_r=16, image_folder=tmp,
+                              hfrm_ckpt=synth_hfrm_checkpoint(61), test_set="raindrop")
+    torch.manual_seed(100 + rank)  # different initial weights per rank: the DDP wrap must broadcast rank 0's
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = DenoisingDiffusion_Wavelet(args, cfg)
+    assert isinstance(d.model, torch.nn.parallel.DistributedDataParallel)
+    w = d.model.module.conv_in.weight.detach().clone()
+    ws = [torch.empty_like(w) for _ in range(world)]
+    dist.all_gather(ws, w)
+    assert all(torch.equal(ws[0], x) for x in ws), "weights were not broadcast from rank 0"
+    # image sharding + gather of restored images to rank 0 (bench.py's N>1 data path)
+    B = 3
+    mine = torch.full((B, 3, 8, 8), float(rank))
+    gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, gathered, dst=0)
+    if rank == 0:
+        assert [float(t.mean()) for t in gathered] == [float(r) for r in range(world)]
+    patches, first = make_patch_table(B, [(0, 0), (0, 4)], "cpu")
+    assert patches.shape == (6, 3) and first[-1].item() == 6
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_weight_broadcast_and_gather(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 400)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
