@@ -75,6 +75,138 @@ struct Cfg {
     static constexpr int kSmem = kStages * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
+// Epilogue of one 128-row x BN accumulator: this thread owns row `row` of m-tile `mt` (TMEM lane = row), `tacc` is the
+// TMEM address of the accumulator's first column for this warp's lane quarter.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const TcArgs& a, uint32_t tacc, int mt, int nt, int ew, int lane, int row) {
+            const long long m = (long long)mt * kBM + row;
+            const bool valid = m < a.M;
+            const float* temb_row = nullptr;
+            if (a.temb) temb_row = a.temb + (a.temb_rows > 1 ? (long long)(m / a.HWout) * a.temb_ld : 0);
+            const bool res16 = a.residual && !a.out_f32 && valid;
+            const uint4* res_ptr = reinterpret_cast<const uint4*>(
+                reinterpret_cast<const __nv_bfloat16*>(a.residual) + (valid ? m : 0) * a.ldr + nt * BN);
+            uint4 res_next[4];
+            if (res16) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) res_next[q] = res_ptr[q];
+            }
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t r[32];
+                uint4 res_cur[4];
+                if (res16) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) res_cur[q] = res_next[q];
+                    if (ch + 1 < BN / 32) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) res_next[q] = res_ptr[(ch + 1) * 4 + q];
+                    }
+                }
+                ptx::tmem_ld_32x32b_x32(tacc + ch * 32, r);
+                ptx::tmem_ld_wait();
+                if (valid) {
+                    const int n = nt * BN + ch * 32;
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * a.alpha;
+                    if (a.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n + j));
+                            v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+                        }
+                    }
+                    if (temb_row) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(temb_row + n + j));
+                            v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+                        }
+                    }
+                    if (a.out_f32) {
+                        if (a.residual) {
+                            const float* rp = reinterpret_cast<const float*>(a.residual) + m * a.ldr + n;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(rp + j);
+                                v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
+                            }
+                        }
+                        float* op = reinterpret_cast<float*>(a.out) + m * a.ldo + n;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+                        if (a.residual) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 u = res_cur[q];
+                                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    v[q * 8 + 2 * i] += __uint_as_float(w[i] << 16);
+                                    v[q * 8 + 2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+                                }
+                            }
+                        }
+                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + m * a.ldo + n);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                __nv_bfloat162 t = __floats2bfloat162_rn(v[q * 8 + 2 * i], v[q * 8 + 2 * i + 1]);
+                                w[i] = *reinterpret_cast<uint32_t*>(&t);
+                            }
+                            op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                    if (a.stats) {
+                        // per 4-column block (sum, sum of squares) of this row ...
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) {
+                            const float x0 = v[4 * b], x1 = v[4 * b + 1], x2 = v[4 * b + 2], x3 = v[4 * b + 3];
+                            r[2 * b] = __float_as_uint((x0 + x1) + (x2 + x3));
+                            r[2 * b + 1] = __float_as_uint(fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3));
+                        }
+                    }
+                } else if (a.stats) {
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) r[b] = 0u;
+                }
+                if (a.stats) {
+                    // ... reduce-scattered over the warp's 32 rows: 16 values, 16 shuffles; lane 2k ends with value k
+                    float s8[8], s4[4], s2[2], s1;
+                    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float keep = __uint_as_float(h16 ? r[i + 8] : r[i]);
+                        const float send = __uint_as_float(h16 ? r[i] : r[i + 8]);
+                        s8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float keep = h8 ? s8[i + 4] : s8[i], send = h8 ? s8[i] : s8[i + 4];
+                        s4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float keep = h4 ? s4[i + 2] : s4[i], send = h4 ? s4[i] : s4[i + 2];
+                        s2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    {
+                        const float keep = h2 ? s2[1] : s2[0], send = h2 ? s2[0] : s2[1];
+                        s1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+                    const long long rg = ((long long)mt * kBM + ew * 32) >> 5;
+                    if (!(lane & 1) && (long long)mt * kBM + ew * 32 < a.M)
+                        a.stats[(rg * (a.N >> 2) + ((nt * BN + ch * 32) >> 2)) * 2 + (lane >> 1)] = s1;
+                }
+            }
+}
+
 template <int BN, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -225,132 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll 1
             for (int hh = 0; hh < MT; ++hh) {
             const int mt = st * MT + hh;
-            const long long m = (long long)mt * kBM + row;
-            const bool valid = m < a.M;
-            const float* temb_row = nullptr;
-            if (a.temb) temb_row = a.temb + (a.temb_rows > 1 ? (long long)(m / a.HWout) * a.temb_ld : 0);
-            const bool res16 = a.residual && !a.out_f32 && valid;
-            const uint4* res_ptr = reinterpret_cast<const uint4*>(
-                reinterpret_cast<const __nv_bfloat16*>(a.residual) + (valid ? m : 0) * a.ldr + nt * BN);
-            uint4 res_next[4];
-            if (res16) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) res_next[q] = res_ptr[q];
-            }
-#pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t r[32];
-                uint4 res_cur[4];
-                if (res16) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) res_cur[q] = res_next[q];
-                    if (ch + 1 < BN / 32) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) res_next[q] = res_ptr[(ch + 1) * 4 + q];
-                    }
-                }
-                ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (as * MT + hh) * BN + ch * 32, r);
-                ptx::tmem_ld_wait();
-                if (valid) {
-                    const int n = nt * BN + ch * 32;
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * a.alpha;
-                    if (a.bias) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n + j));
-                            v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
-                        }
-                    }
-                    if (temb_row) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(temb_row + n + j));
-                            v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
-                        }
-                    }
-                    if (a.out_f32) {
-                        if (a.residual) {
-                            const float* rp = reinterpret_cast<const float*>(a.residual) + m * a.ldr + n;
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(rp + j);
-                                v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
-                            }
-                        }
-                        float* op = reinterpret_cast<float*>(a.out) + m * a.ldo + n;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-                        if (a.residual) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint4 u = res_cur[q];
-                                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    v[q * 8 + 2 * i] += __uint_as_float(w[i] << 16);
-                                    v[q * 8 + 2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
-                                }
-                            }
-                        }
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + m * a.ldo + n);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                __nv_bfloat162 t = __floats2bfloat162_rn(v[q * 8 + 2 * i], v[q * 8 + 2 * i + 1]);
-                                w[i] = *reinterpret_cast<uint32_t*>(&t);
-                            }
-                            op[q] = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                    }
-                    if (a.stats) {
-                        // per 4-column block (sum, sum of squares) of this row ...
-#pragma unroll
-                        for (int b = 0; b < 8; ++b) {
-                            const float x0 = v[4 * b], x1 = v[4 * b + 1], x2 = v[4 * b + 2], x3 = v[4 * b + 3];
-                            r[2 * b] = __float_as_uint((x0 + x1) + (x2 + x3));
-                            r[2 * b + 1] = __float_as_uint(fmaf(x0, x0, x1 * x1) + fmaf(x2, x2, x3 * x3));
-                        }
-                    }
-                } else if (a.stats) {
-#pragma unroll
-                    for (int b = 0; b < 16; ++b) r[b] = 0u;
-                }
-                if (a.stats) {
-                    // ... reduce-scattered over the warp's 32 rows: 16 values, 16 shuffles; lane 2k ends with value k
-                    float s8[8], s4[4], s2[2], s1;
-                    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float keep = __uint_as_float(h16 ? r[i + 8] : r[i]);
-                        const float send = __uint_as_float(h16 ? r[i] : r[i + 8]);
-                        s8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float keep = h8 ? s8[i + 4] : s8[i], send = h8 ? s8[i] : s8[i + 4];
-                        s4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const float keep = h4 ? s4[i + 2] : s4[i], send = h4 ? s4[i] : s4[i + 2];
-                        s2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                    }
-                    {
-                        const float keep = h2 ? s2[1] : s2[0], send = h2 ? s2[0] : s2[1];
-                        s1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                    }
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-                    const long long rg = ((long long)mt * kBM + ew * 32) >> 5;
-                    if (!(lane & 1) && (long long)mt * kBM + ew * 32 < a.M)
-                        a.stats[(rg * (a.N >> 2) + ((nt * BN + ch * 32) >> 2)) * 2 + (lane >> 1)] = s1;
-                }
-            }
+            epilogue_rows<BN>(a, tmem_base + ((uint32_t)(ew * 32) << 16) + (as * MT + hh) * BN, mt, nt, ew, lane, row);
             }  // hh
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[as]);
@@ -361,6 +368,165 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    }
+}
+
+
+// ================================================================================================ CTA-pair kernel
+// cta_group::2: a cluster of two CTAs (one TPC) computes a 256 x BN tile. Each CTA loads its own 128 A rows and HALF of
+// the B tile (BN/2 weight rows); the leader's tcgen05.mma reads both halves, so weight-tile traffic out of L2 is halved
+// per FLOP (the 1-CTA kernel is L2->SM bandwidth bound). Accumulators: 128 lanes x BN columns in each CTA's TMEM,
+// double-buffered. Barriers: both producers signal the LEADER's full[] (tx bytes), the leader's commits are multicast
+// to both CTAs' empty[] / tfull[], and both CTAs' epilogues arrive on the leader's tempty[].
+template <int BN>
+struct Cfg2 {
+    static constexpr int kBBytes = (BN / 2) * kBK * 2;   // this CTA's half of the B tile
+    static constexpr int kStage = kABytes + kBBytes;
+    static constexpr int kStages = kSmemBudget / kStage;
+    static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kSmem = kStages * kStage + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    using C = Cfg2<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStage);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + C::kStages;
+    uint64_t* tfull = bars + 2 * C::kStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmA0);
+        ptx::prefetch_tmap(&tmA1);
+        ptx::prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            ptx::mbar_init(&full[s], 1);
+            ptx::mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(&tfull[s], 1);
+            ptx::mbar_init(&tempty[s], 256);  // 128 epilogue threads of each CTA (only the leader's copy is used)
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc2(tmem_slot, C::kTmemCols);
+        ptx::tmem_relinquish2();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;  // 256-row super-tiles
+    const int kc_per_tap = a.kc0 + a.kc1;
+    const int kblocks = a.taps * kc_per_tap;
+    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        uint32_t it = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += nclusters) {
+            const int st = tile / a.n_tiles, nt = tile - st * a.n_tiles;
+            const int mt = st * 2 + (int)rank;
+            const int m0 = (a.a_shared ? mt % a.tiles_per_batch : mt) * kBM;
+            const int n_img = m0 / a.HWout;
+            const int cy0 = ((m0 - n_img * a.HWout) / a.Wout) * a.stride - a.pad;
+            const int bb = a.b_batched ? (st * 2) / a.tiles_per_batch : 0;
+            const int nrow = nt * BN + (int)rank * (BN / 2);
+            for (int tap = 0; tap < a.taps; ++tap) {
+                const int dy = a.taps == 9 ? tap / 3 : 0, dx = a.taps == 9 ? tap % 3 : 0;
+                const int cx = dx - a.pad;
+                for (int kc = 0; kc < kc_per_tap; ++kc, ++it) {
+                    const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
+                    ptx::mbar_wait(&empty[s], ph ^ 1);
+                    if (lane == 0) {
+                        uint8_t* sa = smem + s * C::kStage;
+                        uint8_t* sb = sa + kABytes;
+                        if (leader) ptx::mbar_arrive_expect_tx(&full[s], 2 * C::kStage);  // bytes of BOTH CTAs
+                        if (kc < a.kc0)
+                            ptx::tma2_load_4d(sa, &tmA0, &full[s], kc * kBK, cx, cy0 + dy, n_img);
+                        else
+                            ptx::tma2_load_4d(sa, &tmA1, &full[s], (kc - a.kc0) * kBK, cx, cy0 + dy, n_img);
+                        const int kcoord = (tap * kc_per_tap + kc) * kBK;
+                        if (a.b_batched)
+                            ptx::tma2_load_3d(sb, &tmB, &full[s], kcoord, nrow, bb);
+                        else
+                            ptx::tma2_load_2d(sb, &tmB, &full[s], kcoord, nrow);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc(256, BN);
+            uint32_t it = 0, tl = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += nclusters, ++tl) {
+                const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+                ptx::mbar_wait(&tempty[as], aph ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
+                    ptx::mbar_wait(&full[s], ph);
+                    ptx::tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = ptx::smem_u32(smem + s * C::kStage);
+                        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + kABytes);
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; ++k)
+                            ptx::umma2_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        ptx::umma2_commit_mc(&empty[s], 3);
+                        if (kb == kblocks - 1) ptx::umma2_commit_mc(&tfull[as], 3);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        const int ew = warp - 4;
+        const int row = ew * 32 + lane;
+        uint32_t tl = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += nclusters, ++tl) {
+            const int st = tile / a.n_tiles, nt = tile - st * a.n_tiles;
+            const int mt = st * 2 + (int)rank;
+            const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+            if (a.residual) {
+                const int esz = a.out_f32 ? 4 : 2;
+                const long long mr = (long long)mt * kBM + row;
+                if (mr < a.M) {
+                    const char* rp = reinterpret_cast<const char*>(a.residual) + (mr * a.ldr + nt * BN) * esz;
+                    for (int b = 0; b < BN * esz; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
+                }
+            }
+            ptx::mbar_wait(&tfull[as], aph);
+            ptx::tc_fence_after();
+            epilogue_rows<BN>(a, tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN, mt, nt, ew, lane, row);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive_cluster(&tempty[as], 0);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc2(tmem_base, C::kTmemCols);
     }
 }
 
@@ -410,6 +576,18 @@ int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& B
     const int tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;
     const int grid = tiles < num_sms_tc() ? tiles : num_sms_tc();
     gemm_tc_kernel<BN, MT><<<grid, kThreads, C::kSmem, s>>>(A0, A1, B, a);
+    return wdm_launch_status();
+}
+
+template <int BN>
+int launch_pair(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& B, const TcArgs& a, cudaStream_t s) {
+    using C = Cfg2<BN>;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    if (e != cudaSuccess) return wdm_cuda_error((int)e);
+    const int tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
+    const int pairs = num_sms_tc() / 2;
+    const int grid = 2 * (tiles < pairs ? tiles : pairs);
+    gemm_tc2_kernel<BN><<<grid, kThreads, C::kSmem, s>>>(A0, A1, B, a);
     return wdm_launch_status();
 }
 
@@ -469,6 +647,14 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     const int HWout = p.Hout * p.Wout;
     const int npatch = p.a_shared ? 1 : (p.M + HWout - 1) / HWout;
     const int BN = pick_bn(p.N);
+    static const int pair_enabled = []() {
+        const char* e = getenv("WDM_TC_PAIR");
+        return e ? atoi(e) : 1;
+    }();
+    const int tiles_per_batch_h = p.b_batch_stride ? HWout / kBM : 0;
+    // CTA pairs (cta_group::2) for the 256-wide N tiles: halves the weight-tile traffic out of L2
+    const bool use_pair = pair_enabled && BN == 256 && (!p.b_batch_stride || tiles_per_batch_h % 2 == 0);
+    const int b_box_rows = use_pair ? BN / 2 : BN;
 
     CUtensorMap A0, A1, B;
     auto make_a = [&](CUtensorMap* m, const void* src, int C, int ld) -> int {
@@ -491,12 +677,12 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         const int nb = p.M / HWout;
         uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.N, (uint64_t)nb};
         uint64_t strides[2] = {(uint64_t)p.ldb * 2, (uint64_t)p.b_batch_stride * 2};
-        uint32_t box[3] = {(uint32_t)kBK, (uint32_t)BN, 1};
+        uint32_t box[3] = {(uint32_t)kBK, (uint32_t)b_box_rows, 1};
         r = make_tmap(&B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.B, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     } else {
         uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
         uint64_t strides[1] = {(uint64_t)p.ldb * 2};
-        uint32_t box[2] = {(uint32_t)kBK, (uint32_t)BN};
+        uint32_t box[2] = {(uint32_t)kBK, (uint32_t)b_box_rows};
         r = make_tmap(&B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.B, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     }
@@ -518,6 +704,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     a.out_f32 = p.out_dtype == DT_F32;
     a.stats = p.stats_out;
     a.N = p.N;
+    if (use_pair) return launch_pair<256>(A0, A1, B, a, s);
     const bool allow2 = !a.b_batched || (a.tiles_per_batch % 2 == 0);
     const int MT = g_force_mt ? (g_force_mt == 2 && allow2 && BN != 64 ? 2 : 1) : pick_mt(a.m_tiles, a.n_tiles, BN, allow2);
     if (BN == 256) return MT == 2 ? launch_bn<256, 2>(A0, A1, B, a, s) : launch_bn<256, 1>(A0, A1, B, a, s);
