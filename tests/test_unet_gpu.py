@@ -167,6 +167,71 @@ def test_gemm_tc_conv_cases(case):
     assert (out - outs).abs().max().item() <= 1e-2 * scale
 
 
+@pytest.mark.parametrize("case", [(2, 256, 256, 16), (64, 768, 768, 8), (2, 128, 128, 32), (4, 64, 256, 8)])
+def test_gemm_tc_subpixel_upsample_conv(case):
+    """nearest-x2 upsample + 3x3 conv evaluated as four 2x2 phase convs on the source grid (ups = 2) equals
+    F.interpolate + conv2d; its GroupNorm side-car sums to the sums of the output."""
+    P, C, Cout, H = case
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(23)
+    rb = lambda t: t.bfloat16().float()
+    x = rb(torch.randn(P, C, H, H, generator=g))
+    w = torch.randn(Cout, C, 3, 3, generator=g) / (3 * C ** 0.5)
+    bias = torch.randn(Cout, generator=g)
+    # phase weights, summed in fp32 then rounded to bf16 (what wdm_unet_create packs)
+    rows = {0: [[0], [1, 2]], 1: [[0, 1], [2]]}
+    wp = torch.zeros(4, Cout, 4, C)
+    for py in (0, 1):
+        for px in (0, 1):
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = torch.zeros(Cout, C)
+                    for yy in rows[py][ty]:
+                        for xx in rows[px][tx]:
+                            acc += w[:, :, yy, xx]
+                    wp[py * 2 + px, :, ty * 2 + tx, :] = acc
+    wp = rb(wp)
+    # reference: the same (rounded) phase weights applied as 2x2 convs == upsample + conv with the unrounded sum
+    ref = torch.zeros(P, Cout, 2 * H, 2 * H)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for py in (0, 1):
+        for px in (0, 1):
+            k = wp[py * 2 + px].reshape(Cout, 2, 2, C).permute(0, 3, 1, 2)   # [Cout][C][ty][tx]
+            y = F.conv2d(xp[:, :, py:py + H + 1, px:px + H + 1], k, bias)    # rows i+py-1+ty  (padded index +1)
+            ref[:, :, py::2, px::2] = y
+    direct = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, bias, padding=1)
+    assert (ref - direct).abs().max().item() <= 3e-2 * max(1.0, direct.abs().max().item())  # bf16 weight rounding only
+    xa = x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)
+    wd = wp.reshape(4 * Cout, 4 * C).contiguous().to(DEV, torch.bfloat16)
+    out = torch.empty(P, 2 * H, 2 * H, Cout, device=DEV, dtype=torch.bfloat16)
+    bd = bias.to(DEV)
+    M = P * 4 * H * H
+    stats = torch.full((M // 32, Cout // 4, 2), float("nan"), device=DEV)
+    p = GemmParams()
+    p.src0, p.C0, p.ld0 = xa.data_ptr(), C, C
+    p.Hin, p.Win, p.Hout, p.Wout = H, H, 2 * H, 2 * H
+    p.taps, p.stride, p.pad, p.ups = 4, 1, 0, 2
+    p.B, p.ldb, p.b_layout = wd.data_ptr(), 4 * C, 0
+    p.M, p.N, p.K = M, Cout, 4 * C
+    p.alpha, p.bias = 1.0, bd.data_ptr()
+    p.out, p.ldo = out.data_ptr(), Cout
+    p.a_dtype = p.b_dtype = p.out_dtype = 1
+    p.stats_out = stats.data_ptr()
+    _lib.check(lib.wdm_gemm(ctypes.byref(p), _lib.WDM_GEMM_IMPL_TC, torch.cuda.current_stream().cuda_stream), "wdm_gemm")
+    torch.cuda.synchronize()
+    res = out.float().permute(0, 3, 1, 2).cpu()
+    scale = max(1.0, ref.abs().max().item())
+    assert (res - ref).abs().max().item() <= 6e-3 * scale
+    st = stats.cpu()
+    assert not torch.isnan(st).any()
+    # per patch, per 4-channel block: the side-car sums equal the sums over the patch's output pixels
+    per_patch = st.reshape(P, (4 * H * H) // 32, Cout // 4, 2).sum(1)
+    rsum = ref.reshape(P, Cout // 4, 4, -1).sum(dim=(2, 3))
+    rsq = (ref ** 2).reshape(P, Cout // 4, 4, -1).sum(dim=(2, 3))
+    assert (per_patch[..., 0] - rsum).abs().max().item() <= 2e-3 * max(1.0, rsum.abs().max().item())
+    assert (per_patch[..., 1] - rsq).abs().max().item() <= 2e-3 * max(1.0, rsq.abs().max().item())
+
+
 @pytest.mark.parametrize("case", [(2, 128, 0, 256, 16, 3, 1, 0, 1, True), (4, 128, 0, 768, 8, 1, 1, 0, 0, False),
                                   (1, 128, 0, 128, 64, 3, 1, 0, 0, False)])
 def test_gemm_tc_groupnorm_sidecar(case):

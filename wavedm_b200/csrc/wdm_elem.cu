@@ -443,9 +443,47 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
         *reinterpret_cast<__nv_bfloat16*>(d) = __float2bfloat16(v);
 }
 
+// nearest-x2-upsample followed by a 3x3 conv == four 2x2 convs on the source grid, one per output phase (py, px):
+//   out[2i+py][2j+px] = sum_{ty,tx} Wp[py][px][ty][tx] . x[i + py - 1 + ty][j + px - 1 + tx]
+//   Wp[0][.][0] = W[0], Wp[0][.][1] = W[1] + W[2];  Wp[1][.][0] = W[0] + W[1], Wp[1][.][1] = W[2]   (rows; same for columns)
+// w: OIHW fp32 [Cout][Cin][3][3]  ->  out[ph][Cout][t][Cin], ph = 2 py + px, t = 2 ty + tx (summed in fp32, then rounded)
+template <typename TO>
+__global__ void pack_subpix_weight_kernel(const float* __restrict__ w, int Cout, int Cin, TO* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = 16LL * Cout * Cin;
+    if (i >= total) return;
+    const int ci = (int)(i % Cin);
+    long long r = i / Cin;
+    const int t = (int)(r % 4);
+    r /= 4;
+    const int co = (int)(r % Cout);
+    const int ph = (int)(r / Cout);
+    const int py = ph >> 1, px = ph & 1, ty = t >> 1, tx = t & 1;
+    const int y0 = py == 0 ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), y1 = py == 0 ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+    const int x0 = px == 0 ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), x1 = px == 0 ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+    const float* wp = w + ((long long)co * Cin + ci) * 9;
+    float acc = 0.f;
+    for (int y = y0; y <= y1; ++y)
+        for (int x = x0; x <= x1; ++x) acc += wp[y * 3 + x];
+    if (sizeof(TO) == 4)
+        reinterpret_cast<float*>(out)[i] = acc;
+    else
+        reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16(acc);
+}
+
 }  // namespace
 
 // ================================================================================================ launchers
+int launch_pack_subpix_weight(const float* w, int Cout, int Cin, void* out, int out_dtype, cudaStream_t s) {
+    const long long total = 16LL * Cout * Cin;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (out_dtype == DT_F32)
+        pack_subpix_weight_kernel<float><<<grid, 256, 0, s>>>(w, Cout, Cin, reinterpret_cast<float*>(out));
+    else
+        pack_subpix_weight_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(out));
+    return wdm_launch_status();
+}
+
 static int pick_slabs(int P, int HW) {
     int S = 1;
     while (S < kMaxSlabs && P * S < 2 * 148 && HW / (S * 2) >= 16 && HW % (S * 2) == 0) S *= 2;

@@ -51,6 +51,7 @@ struct TcArgs {
     int out_f32;
     float* stats;   // GroupNorm side-car [M/32][N/4][2] or null
     int N;
+    int subpix;     // nearest-x2-upsample + 3x3 conv as 4 output-phase 2x2 convs (m-tiles are phase-major)
 };
 
 // K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1).
@@ -81,6 +82,19 @@ template <int BN>
 __device__ __forceinline__ void epilogue_rows(const TcArgs& a, uint32_t tacc, int mt, int nt, int ew, int lane, int row) {
             const long long m = (long long)mt * kBM + row;
             const bool valid = m < a.M;
+            long long orow = m;        // row of `out` this thread writes
+            long long rg_base = ((long long)mt * kBM + ew * 32) >> 5;  // side-car row group of this warp
+            if (a.subpix) {
+                // m-space is (phase, patch, i, j) over the SOURCE grid; the output pixel is (2i+py, 2j+px)
+                const int ph = mt / a.tiles_per_batch;
+                const int msrc = (mt - ph * a.tiles_per_batch) * kBM + row;
+                const int n_img = msrc / a.HWout, rem = msrc - n_img * a.HWout;
+                const int i = rem / a.Wout, j = rem - i * a.Wout;
+                orow = ((long long)n_img * (a.HWout / a.Wout) * 2 + 2 * i + (ph >> 1)) * (2 * a.Wout) + 2 * j + (ph & 1);
+                const int msrc_w = (mt - ph * a.tiles_per_batch) * kBM + ew * 32;
+                const int n_w = msrc_w / a.HWout;
+                rg_base = (long long)n_w * (a.HWout >> 3) + (long long)ph * (a.HWout >> 5) + ((msrc_w - n_w * a.HWout) >> 5);
+            }
             const float* temb_row = nullptr;
             if (a.temb) temb_row = a.temb + (a.temb_rows > 1 ? (long long)(m / a.HWout) * a.temb_ld : 0);
             const bool res16 = a.residual && !a.out_f32 && valid;
@@ -133,7 +147,7 @@ __device__ __forceinline__ void epilogue_rows(const TcArgs& a, uint32_t tacc, in
                                 v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
                             }
                         }
-                        float* op = reinterpret_cast<float*>(a.out) + m * a.ldo + n;
+                        float* op = reinterpret_cast<float*>(a.out) + orow * a.ldo + n;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -150,7 +164,7 @@ __device__ __forceinline__ void epilogue_rows(const TcArgs& a, uint32_t tacc, in
                                 }
                             }
                         }
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + m * a.ldo + n);
+                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + orow * a.ldo + n);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             uint32_t w[4];
@@ -200,7 +214,7 @@ __device__ __forceinline__ void epilogue_rows(const TcArgs& a, uint32_t tacc, in
                         s1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
                     }
                     s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-                    const long long rg = ((long long)mt * kBM + ew * 32) >> 5;
+                    const long long rg = rg_base;
                     if (!(lane & 1) && (long long)mt * kBM + ew * 32 < a.M)
                         a.stats[(rg * (a.N >> 2) + ((nt * BN + ch * 32) >> 2)) * 2 + (lane >> 1)] = s1;
                 }
@@ -273,7 +287,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             int kb_lin = 0;
             for (int tap = 0; tap < a.taps; ++tap) {
-                const int dy = a.taps == 9 ? tap / 3 : 0, dx = a.taps == 9 ? tap % 3 : 0;
+                int dy = a.taps == 9 ? tap / 3 : 0, dx = a.taps == 9 ? tap % 3 : 0;
+                if (a.subpix) dy = (bb >> 1) - 1 + (tap >> 1), dx = (bb & 1) - 1 + (tap & 1);  // bb = output phase
                 const int cx = dx - a.pad;
                 for (int kc = 0; kc < kc_per_tap; ++kc, ++it) {
                     const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
@@ -447,7 +462,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const int bb = a.b_batched ? (st * 2) / a.tiles_per_batch : 0;
             const int nrow = nt * BN + (int)rank * (BN / 2);
             for (int tap = 0; tap < a.taps; ++tap) {
-                const int dy = a.taps == 9 ? tap / 3 : 0, dx = a.taps == 9 ? tap % 3 : 0;
+                int dy = a.taps == 9 ? tap / 3 : 0, dx = a.taps == 9 ? tap % 3 : 0;
+                if (a.subpix) dy = (bb >> 1) - 1 + (tap >> 1), dx = (bb & 1) - 1 + (tap & 1);  // bb = output phase
                 const int cx = dx - a.pad;
                 for (int kc = 0; kc < kc_per_tap; ++kc, ++it) {
                     const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
@@ -608,14 +624,20 @@ int pick_mt(int m_tiles, int n_tiles, int BN, bool allow2) {
 bool gemm_tc_supported(const GemmParams& p) {
     if (p.a_dtype != DT_BF16 || p.b_dtype != DT_BF16) return false;
     if (p.out_dtype != DT_BF16 && p.out_dtype != DT_F32) return false;
-    if (p.b_layout != BL_NK || p.ups) return false;
+    if (p.b_layout != BL_NK || (p.ups != 0 && p.ups != 2)) return false;
+    if (p.ups == 2) {
+        // sub-pixel upsample-conv: B = [4 phases][N][4*C0], geometry is tiled on the SOURCE grid
+        if (p.taps != 4 || p.C1 || p.stride != 1 || p.temb || p.residual || p.b_batch_stride || p.a_shared) return false;
+        if (p.Hout != 2 * p.Hin || p.Wout != 2 * p.Win || ((p.Hin * p.Win) % 32) || (p.M % (4 * kBM))) return false;
+        if (pick_bn(p.N) != 256 && ((p.M / 4 / kBM) % 2)) return false;
+    }
     if ((p.C0 % kBK) || (p.C1 % kBK) || p.C0 <= 0) return false;
-    if (p.taps != 1 && p.taps != 9) return false;
+    if (p.taps != 1 && p.taps != 9 && !(p.taps == 4 && p.ups == 2)) return false;
     if (p.stride != 1 && p.stride != 2) return false;
     if (p.taps == 1 && p.stride != 1) return false;
     if (!pick_bn(p.N)) return false;
     Geom g;
-    if (!tile_geom(p.Hout, p.Wout, &g)) return false;
+    if (!tile_geom(p.ups == 2 ? p.Hin : p.Hout, p.ups == 2 ? p.Win : p.Wout, &g)) return false;
     if (p.stride == 2 && (2 * g.Wb > 256 || 2 * g.Hb > 256)) return false;
     if (p.b_batch_stride) {
         if ((p.Hout * p.Wout) % kBM) return false;
@@ -642,18 +664,22 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         g_force_mt = forced;
     }
     if (p.M <= 0) return WDM_OK;
+    const bool subpix = p.ups == 2;
     Geom g;
-    tile_geom(p.Hout, p.Wout, &g);
-    const int HWout = p.Hout * p.Wout;
-    const int npatch = p.a_shared ? 1 : (p.M + HWout - 1) / HWout;
+    // m-space grid: the output grid, or the SOURCE grid for the sub-pixel upsample-conv (4 phases x source pixels)
+    const int Hm = subpix ? p.Hin : p.Hout, Wm = subpix ? p.Win : p.Wout;
+    tile_geom(Hm, Wm, &g);
+    const int HWout = Hm * Wm;
+    const int npatch = p.a_shared ? 1 : (subpix ? p.M / (4 * HWout) : (p.M + HWout - 1) / HWout);
     const int BN = pick_bn(p.N);
     static const int pair_enabled = []() {
         const char* e = getenv("WDM_TC_PAIR");
         return e ? atoi(e) : 1;
     }();
-    const int tiles_per_batch_h = p.b_batch_stride ? HWout / kBM : 0;
+    const int tiles_per_batch_h = subpix ? p.M / 4 / kBM : (p.b_batch_stride ? HWout / kBM : 0);
     // CTA pairs (cta_group::2) for the 256-wide N tiles: halves the weight-tile traffic out of L2
-    const bool use_pair = pair_enabled && BN == 256 && (!p.b_batch_stride || tiles_per_batch_h % 2 == 0);
+    const bool use_pair =
+        pair_enabled && BN == 256 && ((!p.b_batch_stride && !subpix) || tiles_per_batch_h % 2 == 0);
     const int b_box_rows = use_pair ? BN / 2 : BN;
 
     CUtensorMap A0, A1, B;
@@ -673,10 +699,11 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     } else {
         A1 = A0;
     }
-    if (p.b_batch_stride) {
-        const int nb = p.M / HWout;
+    if (p.b_batch_stride || subpix) {
+        const int nb = subpix ? 4 : p.M / HWout;
+        const long long bstride = subpix ? (long long)p.N * p.ldb : p.b_batch_stride;
         uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.N, (uint64_t)nb};
-        uint64_t strides[2] = {(uint64_t)p.ldb * 2, (uint64_t)p.b_batch_stride * 2};
+        uint64_t strides[2] = {(uint64_t)p.ldb * 2, (uint64_t)bstride * 2};
         uint32_t box[3] = {(uint32_t)kBK, (uint32_t)b_box_rows, 1};
         r = make_tmap(&B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, p.B, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     } else {
@@ -694,10 +721,11 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     a.M = p.M;
     a.kc0 = p.C0 / kBK, a.kc1 = p.C1 / kBK;
     a.taps = p.taps, a.stride = p.stride, a.pad = p.pad;
-    a.Wout = p.Wout, a.HWout = HWout;
-    a.b_batched = p.b_batch_stride ? 1 : 0;
-    a.tiles_per_batch = p.b_batch_stride ? HWout / kBM : 0;
-    a.a_shared = p.a_shared ? 1 : 0;
+    a.Wout = Wm, a.HWout = HWout;
+    a.b_batched = (p.b_batch_stride || subpix) ? 1 : 0;
+    a.tiles_per_batch = tiles_per_batch_h;
+    a.a_shared = (p.a_shared || subpix) ? 1 : 0;  // in-kernel meaning: the A tile index wraps per batch / phase
+    a.subpix = subpix ? 1 : 0;
     a.alpha = p.alpha;
     a.bias = p.bias, a.temb = p.temb, a.temb_rows = p.temb_rows, a.temb_ld = p.temb_ld;
     a.residual = p.residual, a.ldr = p.ldr, a.out = p.out, a.ldo = p.ldo;

@@ -30,6 +30,7 @@ struct ConvSpec {
     void* pw = nullptr;       // packed weights [Cout][taps*Cin_pad] in engine dtype
     float* pb = nullptr;      // bias fp32 [Cout]
     float* pw32 = nullptr;    // fp32 copy (conv_out only)
+    void* pw_subpix = nullptr;  // upsample convs, bf16 mode: [4 phases][Cout][4 taps][Cin] (sub-pixel decomposition)
 };
 struct GnSpec {
     int C = 0, w = -1, b = -1;
@@ -377,7 +378,15 @@ int pack_model(wdm_unet* net, const float* flat, cudaStream_t s, size_t* total) 
     for (auto& lv : m.up) {
         for (auto& r : lv.blocks) pack_res(r);
         for (auto& a : lv.attns) pack_attn(a);
-        if (lv.has_resample) pack_conv(lv.resample, lv.resample.Cin);
+        if (lv.has_resample) {
+            pack_conv(lv.resample, lv.resample.Cin);
+            if (dt == DT_BF16) {
+                ConvSpec& c = lv.resample;
+                c.pw_subpix = take((size_t)16 * c.Cout * c.Cin * es);
+                if (fill && st == WDM_OK)
+                    st = launch_pack_subpix_weight(flat + m.params[c.w].off, c.Cout, c.Cin, c.pw_subpix, dt, s);
+            }
+        }
     }
     pack_gn(m.norm_out);
     // conv_out: fp32 [Cout][9][C] for the small-Cout kernel
@@ -496,6 +505,32 @@ Act gn_op(Ctx& c, const Act& a, const Act* a2, const GnSpec& g, int silu) {
             c.fail(launch_gn_apply(a.p, a.C, a2 ? a2->p : nullptr, a2 ? a2->C : 0, c.net->dt, c.P, a.H * a.W,
                                    c.gn_scratch, g.gamma, g.beta, silu, o.p, c.s));
     }
+    return o;
+}
+
+// models/unet.py:51-56 on the tensor-core path: nearest x2 upsample + 3x3 conv as four 2x2 phase convs on the source
+// grid (2.25x fewer FLOPs, no materialised 4x tensor). Returns an empty Act (C == 0) when the shape is not supported.
+Act upsample_conv_subpix(Ctx& c, const Act& a, const ConvSpec& w) {
+    Act none;
+    if (!w.pw_subpix) return none;
+    GemmParams p;
+    memset(&p, 0, sizeof p);
+    p.src0 = a.p, p.C0 = a.C, p.ld0 = a.C;
+    p.Hin = a.H, p.Win = a.W, p.Hout = 2 * a.H, p.Wout = 2 * a.W;
+    p.taps = 4, p.stride = 1, p.pad = 0, p.ups = 2;
+    p.B = w.pw_subpix, p.ldb = 4 * w.Cin, p.b_layout = BL_NK;
+    p.M = c.P * p.Hout * p.Wout, p.N = w.Cout, p.K = 4 * a.C;
+    p.alpha = 1.f, p.bias = w.pb;
+    p.ldo = w.Cout;
+    p.a_dtype = p.b_dtype = p.out_dtype = c.net->dt;
+    p.out = reinterpret_cast<void*>(16);  // placeholder for the support check (alignment only)
+    if (!will_use_tc(c, p)) return none;
+    Act o = new_act(c, p.Hout, p.Wout, w.Cout);
+    p.out = o.p;
+    o.stats = reinterpret_cast<float*>(c.ar->alloc((size_t)(p.M / 32) * (p.N / 4) * 2 * sizeof(float)));
+    if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
+    p.stats_out = o.stats;
+    run_gemm(c, p);
     return o;
 }
 
@@ -682,6 +717,8 @@ int forward_impl(wdm_unet* net, Arena* ar, const void* x, const float* t, int T,
             Act h2;
             if (fold_ups) {
                 h2 = conv_op(c, h, nullptr, m.up[lv].resample, 1, 1, nullptr, nullptr, true);
+            } else if (Act sp = upsample_conv_subpix(c, h, m.up[lv].resample); sp.p || (c.dry() && sp.C)) {
+                h2 = sp;
             } else {
                 Act u = new_act(c, h.H * 2, h.W * 2, h.C);
                 if (!c.dry() && c.st == WDM_OK) c.fail(launch_upsample2x(h.p, net->dt, P, h.H, h.W, h.C, u.p, s));
