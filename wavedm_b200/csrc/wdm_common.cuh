@@ -27,6 +27,34 @@ static inline int wdm_launch_status() {
     return WDM_OK;
 }
 
+#ifdef __CUDACC__
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream drains (its prologue
+// -- barrier init, TMEM allocation, descriptor prefetch -- overlaps the predecessor's tail); it must execute
+// wdm_grid_dependency_wait() before touching anything the predecessor wrote.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t wdm_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                         Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// Called first by every PDL kernel: lets the NEXT kernel's CTAs be scheduled as soon as SM resources allow (they park
+// in wdm_grid_dependency_wait() until this grid has completed). The trigger fires once all CTAs of this grid have
+// executed it, i.e. when the whole grid is resident -- later waves are never starved by parked dependents.
+__device__ __forceinline__ void wdm_grid_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void wdm_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 static inline bool wdm_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 static inline int wdm_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
                                                        const float* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, T* __restrict__ out) {
+    wdm_grid_launch_dependents();
+    wdm_grid_dependency_wait();
     const int C = C0 + C1, nvec = C / V, cpg = C / 32;
     const int p = blockIdx.y;
     const int vec = threadIdx.x % nvec, lane_pix = threadIdx.x / nvec, ppi = blockDim.x / nvec;
@@ -201,6 +203,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
 __global__ void __launch_bounds__(256) gn_finalize_sidecar_kernel(const float* __restrict__ sc0, int C0,
                                                                   const float* __restrict__ sc1, int C1, int HW,
                                                                   int P, double eps, float* __restrict__ stats) {
+    wdm_grid_launch_dependents();
+    wdm_grid_dependency_wait();
     const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= P * 32) return;
     const int lane = threadIdx.x & 31;
@@ -275,6 +279,8 @@ __global__ void upsample2x_kernel(const T* __restrict__ src, int P, int H, int W
 template <typename TO>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, long long rows, int L,
                                                            TO* __restrict__ out) {
+    wdm_grid_launch_dependents();
+    wdm_grid_dependency_wait();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -530,10 +536,8 @@ int launch_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtyp
     if (pix_per_cta > HW) pix_per_cta = HW;
     dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, P);
 #define WDM_GN_APPLY(T, SILU, PREC)                                                                               \
-    gn_apply_kernel<T, 8, SILU, PREC><<<grid, g.threads, 0, s>>>(reinterpret_cast<const T*>(src0), C0,             \
-                                                                 reinterpret_cast<const T*>(src1), C1, HW,         \
-                                                                 pix_per_cta, stats, gamma, beta,                  \
-                                                                 reinterpret_cast<T*>(out))
+    wdm_launch_pdl(gn_apply_kernel<T, 8, SILU, PREC>, grid, dim3(g.threads), 0, s, reinterpret_cast<const T*>(src0), C0, \
+                   reinterpret_cast<const T*>(src1), C1, HW, pix_per_cta, stats, gamma, beta, reinterpret_cast<T*>(out))
     if (dtype == DT_F32) {
         if (silu) WDM_GN_APPLY(float, true, true); else WDM_GN_APPLY(float, false, true);
     } else {
@@ -547,7 +551,8 @@ int launch_gn_finalize_sidecar(const float* sc0, int C0, const float* sc1, int C
                                float* stats, cudaStream_t s) {
     if (((C0 + C1) % 128) || (C0 % 4) || (C1 % 4) || (HW % 32) || !sc0 || (C1 && !sc1)) return WDM_ERR_BAD_SHAPE;
     const int warps = P * 32;
-    gn_finalize_sidecar_kernel<<<(warps + 7) / 8, 256, 0, s>>>(sc0, C0, sc1, C1, HW, P, (double)eps, stats);
+    wdm_launch_pdl(gn_finalize_sidecar_kernel, dim3((warps + 7) / 8), dim3(256), 0, s, sc0, C0, sc1, C1, HW, P, (double)eps,
+                   stats);
     return wdm_launch_status();
 }
 
@@ -570,9 +575,10 @@ int launch_softmax_rows(const float* S, int rows, int L, void* out, int out_dtyp
     if (L % 32 || L > 1024) return WDM_ERR_BAD_SHAPE;
     const unsigned grid = (unsigned)((rows + 7) / 8);
     if (out_dtype == DT_F32)
-        softmax_rows_kernel<float><<<grid, 256, 0, s>>>(S, rows, L, reinterpret_cast<float*>(out));
+        wdm_launch_pdl(softmax_rows_kernel<float>, dim3(grid), dim3(256), 0, s, S, (long long)rows, L, reinterpret_cast<float*>(out));
     else
-        softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(S, rows, L, reinterpret_cast<__nv_bfloat16*>(out));
+        wdm_launch_pdl(softmax_rows_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, S, (long long)rows, L,
+                       reinterpret_cast<__nv_bfloat16*>(out));
     return wdm_launch_status();
 }
 

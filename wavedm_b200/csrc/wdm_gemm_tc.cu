@@ -236,6 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    wdm_grid_launch_dependents();
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA0);
         ptx::prefetch_tmap(&tmA1);
@@ -260,6 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    wdm_grid_dependency_wait();  // PDL: everything above overlapped the previous kernel's tail
 
     const int num_tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;  // super-tiles of MT m-tiles
     const int kc_per_tap = a.kc0 + a.kc1;
@@ -444,6 +446,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     ptx::cluster_sync_all();  // peer barriers are initialised before any remote arrive / TMA signal
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    wdm_grid_dependency_wait();  // PDL: everything above overlapped the previous kernel's tail
 
     const int num_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;  // 256-row super-tiles
     const int kc_per_tap = a.kc0 + a.kc1;
@@ -591,7 +594,8 @@ int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& B
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     const int tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;
     const int grid = tiles < num_sms_tc() ? tiles : num_sms_tc();
-    gemm_tc_kernel<BN, MT><<<grid, kThreads, C::kSmem, s>>>(A0, A1, B, a);
+    e = wdm_launch_pdl(gemm_tc_kernel<BN, MT>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, B, a);
+    if (e != cudaSuccess) return wdm_cuda_error((int)e);
     return wdm_launch_status();
 }
 
@@ -603,7 +607,8 @@ int launch_pair(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap&
     const int tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
     const int pairs = num_sms_tc() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    gemm_tc2_kernel<BN><<<grid, kThreads, C::kSmem, s>>>(A0, A1, B, a);
+    e = wdm_launch_pdl(gemm_tc2_kernel<BN>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, B, a);
+    if (e != cudaSuccess) return wdm_cuda_error((int)e);
     return wdm_launch_status();
 }
 
