@@ -421,6 +421,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const bool leader = rank == 0;
+    wdm_grid_launch_dependents();
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA0);
         ptx::prefetch_tmap(&tmA1);
