@@ -173,6 +173,13 @@ typedef struct wdm_gemm_params {
     /* != 0: the A operand is ONE matrix shared by every batch (rows m % (Hout*Wout)); used with a per-batch B to
      * compute V^T = Wv * h^T for attention. */
     int a_shared;
+    /* != 0: sources 1 and 2 are 1x1 "tails" appended after the main taps instead of channel-concatenated inputs:
+     *   K = taps*C0 + C1 + C2,  A[m][taps*C0 + c] = (c < C1 ? src1 : src2)[pixel m][c]   (centre tap, stride 1)
+     * This is conv2 + nin_shortcut of a ResnetBlock (models/unet.py:128-138) as ONE contraction:
+     *   x + conv2(h) with x = nin(cat[x1, x2])  ==  [W2 | Wnin] . [im2col(h) ; x1 ; x2] + (b2 + bnin). */
+    int tail_1x1;
+    const void* src2;
+    int C2, ld2;
 } wdm_gemm_params;
 #define WDM_GEMM_IMPL_SIMT 0
 #define WDM_GEMM_IMPL_TC 1

@@ -27,7 +27,8 @@ class GemmParams(ctypes.Structure):
         [(n, ctypes.c_int) for n in ("ldb", "b_layout", "M", "N", "K")] + \
         [("alpha", ctypes.c_float), ("bias", ctypes.c_void_p), ("temb", ctypes.c_void_p), ("temb_rows", ctypes.c_int),
          ("temb_ld", ctypes.c_int), ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int), ("out", ctypes.c_void_p)] + \
-        [(n, ctypes.c_int) for n in ("ldo", "a_dtype", "b_dtype", "out_dtype")] + [("stats_out", ctypes.c_void_p), ("a_shared", ctypes.c_int)]
+        [(n, ctypes.c_int) for n in ("ldo", "a_dtype", "b_dtype", "out_dtype")] + [("stats_out", ctypes.c_void_p), ("a_shared", ctypes.c_int), ("tail_1x1", ctypes.c_int),
+                                                                                ("src2", ctypes.c_void_p), ("C2", ctypes.c_int), ("ld2", ctypes.c_int)]
 
 
 def run_conv(x, x2, w, bias, stride, ups, temb, residual, dtype, impl, want_stats=False):
@@ -132,7 +133,7 @@ TC_CASES = [
     # P, C0, C1, Cout, H, k, stride, ups, temb_rows, residual
     (2, 128, 0, 128, 16, 3, 1, 0, 0, False),    # BN=128, 2 rows of 64.. (16x16: 8 rows per tile)
     (3, 128, 0, 256, 16, 3, 1, 0, 1, True),     # BN=256, broadcast temb, residual, M = 768 (6 tiles)
-    (2, 128, 128, 256, 8, 3, 1, 0, 2, True),    # concat (two tensor maps), per-patch temb, 8x8 -> 2 patches per tile
+    (2, 128, 0, 256, 8, 3, 1, 0, 2, True),      # per-patch temb + residual, 8x8 -> 2 patches per tile
     (4, 256, 128, 128, 8, 1, 1, 0, 0, True),    # 1x1 over a concat
     (2, 128, 0, 128, 16, 3, 2, 0, 0, False),    # stride-2 via TMA element strides (out 8x8)
     (2, 128, 0, 128, 64, 3, 2, 0, 0, False),    # stride-2 64 -> 32
@@ -165,6 +166,47 @@ def test_gemm_tc_conv_cases(case):
     # and it agrees with the CUDA-core kernel on the same data
     outs = run_conv(x, x2, w, bias, stride, ups, temb, res, 1, _lib.WDM_GEMM_IMPL_SIMT)
     assert (out - outs).abs().max().item() <= 1e-2 * scale
+
+
+@pytest.mark.parametrize("case", [(2, 256, 128, 128, 16), (2, 768, 768, 512, 8), (3, 128, 256, 0, 32), (2, 512, 512, 256, 16)])
+@pytest.mark.parametrize("impl", [0, 1])
+def test_gemm_fused_conv2_plus_shortcut(case, impl):
+    """conv2 (3x3) and nin_shortcut (1x1 over cat[x1, x2]) as ONE contraction (tail_1x1): K = 9*C + C1 + C2."""
+    P, C, C1, C2, H = case
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(31)
+    rb = lambda t: t.bfloat16().float()
+    h = rb(torch.randn(P, C, H, H, generator=g))
+    x1 = rb(torch.randn(P, C1, H, H, generator=g))
+    x2 = rb(torch.randn(P, C2, H, H, generator=g)) if C2 else None
+    w2 = rb(torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5))
+    wn = rb(torch.randn(C, C1 + C2, 1, 1, generator=g) / (C1 + C2) ** 0.5)
+    b = torch.randn(C, generator=g)
+    xx = x1 if x2 is None else torch.cat([x1, x2], 1)
+    ref = F.conv2d(h, w2, None, padding=1) + F.conv2d(xx, wn, None) + b[None, :, None, None]
+    nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)
+    hd, x1d = nhwc(h), nhwc(x1)
+    x2d = nhwc(x2) if x2 is not None else None
+    wf = torch.cat([w2.permute(0, 2, 3, 1).reshape(C, 9 * C), wn.reshape(C, C1 + C2)], 1).contiguous().to(DEV, torch.bfloat16)
+    out = torch.empty(P, H, H, C, device=DEV, dtype=torch.bfloat16)
+    bd = b.to(DEV)
+    p = GemmParams()
+    p.src0, p.C0, p.ld0 = hd.data_ptr(), C, C
+    p.src1, p.C1, p.ld1 = x1d.data_ptr(), C1, C1
+    if x2d is not None:
+        p.src2, p.C2, p.ld2 = x2d.data_ptr(), C2, C2
+    p.tail_1x1 = 1
+    p.Hin = p.Hout = p.Win = p.Wout = H
+    p.taps, p.stride, p.pad = 9, 1, 1
+    p.B, p.ldb, p.b_layout = wf.data_ptr(), 9 * C + C1 + C2, 0
+    p.M, p.N, p.K = P * H * H, C, 9 * C + C1 + C2
+    p.alpha, p.bias = 1.0, bd.data_ptr()
+    p.out, p.ldo = out.data_ptr(), C
+    p.a_dtype = p.b_dtype = p.out_dtype = 1
+    _lib.check(lib.wdm_gemm(ctypes.byref(p), impl, torch.cuda.current_stream().cuda_stream), "wdm_gemm")
+    torch.cuda.synchronize()
+    res = out.float().permute(0, 3, 1, 2).cpu()
+    assert (res - ref).abs().max().item() <= 6e-3 * max(1.0, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("case", [(2, 256, 256, 16), (64, 768, 768, 8), (2, 128, 128, 32), (4, 64, 256, 8)])

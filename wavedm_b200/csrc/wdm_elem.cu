@@ -449,6 +449,11 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
         *reinterpret_cast<__nv_bfloat16*>(d) = __float2bfloat16(v);
 }
 
+__global__ void vec_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+
 // nearest-x2-upsample followed by a 3x3 conv == four 2x2 convs on the source grid, one per output phase (py, px):
 //   out[2i+py][2j+px] = sum_{ty,tx} Wp[py][px][ty][tx] . x[i + py - 1 + ty][j + px - 1 + tx]
 //   Wp[0][.][0] = W[0], Wp[0][.][1] = W[1] + W[2];  Wp[1][.][0] = W[0] + W[1], Wp[1][.][1] = W[2]   (rows; same for columns)
@@ -480,6 +485,11 @@ __global__ void pack_subpix_weight_kernel(const float* __restrict__ w, int Cout,
 }  // namespace
 
 // ================================================================================================ launchers
+int launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t s) {
+    vec_add_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, out, n);
+    return wdm_launch_status();
+}
+
 int launch_pack_subpix_weight(const float* w, int Cout, int Cin, void* out, int out_dtype, cudaStream_t s) {
     const long long total = 16LL * Cout * Cin;
     const unsigned grid = (unsigned)((total + 255) / 256);

@@ -101,6 +101,7 @@ int launch_ddim_step(const DdimParams& p, cudaStream_t stream);
 int launch_pack_conv_weight(const float* w, int Cout, int Cin, int taps, int Cin_pad, void* out, int out_dtype,
                             long long ldk, long long k_off, cudaStream_t stream);
 
+int launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t stream);
 // sub-pixel decomposition of (nearest x2 upsample -> 3x3 conv): [4 phases][Cout][4 taps][Cin] (see wdm_elem.cu)
 int launch_pack_subpix_weight(const float* w, int Cout, int Cin, void* out, int out_dtype, cudaStream_t stream);
 

@@ -93,9 +93,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
     const int ab = (a_row_ok && !p.a_shared) ? (int)(am / rows_per_batch) : 0;
     const int ar = a_row_ok ? (int)(am % rows_per_batch) : 0;
     const int aoy = ar / p.Wout, aox = ar % p.Wout;
-    const int Ct = p.C0 + p.C1;
+    const int Ct = p.tail_1x1 ? p.C0 : p.C0 + p.C1;        // channels per tap of the main part
     const int cblocks = Ct / BK;
-    const int nkb = p.taps * cblocks;
+    const int main_kb = p.taps * cblocks;
+    const int nkb = main_kb + (p.tail_1x1 ? (p.C1 + p.C2) / BK : 0);
     const int Hv = p.ups ? 2 * p.Hin : p.Hin, Wv = p.ups ? 2 * p.Win : p.Win;  // virtual (post-upsample) size
 
     // ---- B loader
@@ -105,12 +106,15 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
 
     float ra[8], rb[8];
     auto load_tiles = [&](int kb) {
-        const int tap = kb / cblocks;
-        const int c = (kb - tap * cblocks) * BK;
+        const bool tail = kb >= main_kb;
+        const int tap = tail ? 0 : kb / cblocks;
+        const int c = tail ? (kb - main_kb) * BK : (kb - tap * cblocks) * BK;
         // A
         bool ok = a_row_ok;
         int iy = aoy, ix = aox;
-        if (p.taps == 9) {
+        if (tail) {
+            // 1x1 tail sources: centre pixel of the output position
+        } else if (p.taps == 9) {
             iy = aoy * p.stride + tap / 3 - p.pad;
             ix = aox * p.stride + tap % 3 - p.pad;
             ok = ok && iy >= 0 && iy < Hv && ix >= 0 && ix < Wv;
@@ -121,7 +125,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
         if (p.ups) iy >>= 1, ix >>= 1;
         if (ok) {
             const long long pix = ((long long)ab * p.Hin + iy) * p.Win + ix;
-            if (c < p.C0)
+            if (tail) {
+                if (c < p.C1)
+                    load8<TA>(reinterpret_cast<const TA*>(p.src1) + pix * p.ld1 + c + kh * 8, ra);
+                else
+                    load8<TA>(reinterpret_cast<const TA*>(p.src2) + pix * p.ld2 + (c - p.C1) + kh * 8, ra);
+            } else if (c < p.C0)
                 load8<TA>(reinterpret_cast<const TA*>(p.src0) + pix * p.ld0 + c + kh * 8, ra);
             else
                 load8<TA>(reinterpret_cast<const TA*>(p.src1) + pix * p.ld1 + (c - p.C0) + kh * 8, ra);
@@ -130,7 +139,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
             for (int i = 0; i < 8; ++i) ra[i] = 0.f;
         }
         // B
-        const int k0 = tap * Ct + c;
+        const int k0 = tail ? p.taps * Ct + c : tap * Ct + c;
         if (kBLayout == BL_NK) {
             const int n = n0 + (tid & 127);
             if (n < p.N)
@@ -329,7 +338,13 @@ __global__ void __launch_bounds__(256, 2) conv_small_cout_kernel(const T* __rest
 
 int launch_gemm_simt(const GemmParams& p, cudaStream_t s) {
     if (p.M <= 0 || p.N <= 0) return WDM_OK;
-    if ((p.C0 % BK) || (p.C1 % BK) || (p.N % 8) || p.K != p.taps * (p.C0 + p.C1)) return WDM_ERR_BAD_SHAPE;
+    if ((p.C0 % BK) || (p.C1 % BK) || (p.N % 8)) return WDM_ERR_BAD_SHAPE;
+    if (p.tail_1x1) {
+        if ((p.C2 % BK) || p.K != p.taps * p.C0 + p.C1 + p.C2 || p.stride != 1 || p.ups || (p.C2 && !p.src2) || !p.src1)
+            return WDM_ERR_BAD_SHAPE;
+    } else if (p.K != p.taps * (p.C0 + p.C1)) {
+        return WDM_ERR_BAD_SHAPE;
+    }
     if (p.taps != 1 && p.taps != 9) return WDM_ERR_BAD_SHAPE;
     if (p.a_dtype == DT_F32 && p.b_dtype == DT_F32 && p.out_dtype == DT_F32) return launch_t<float, float, float>(p, s);
     if (p.a_dtype == DT_BF16 && p.b_dtype == DT_BF16 && p.out_dtype == DT_BF16)

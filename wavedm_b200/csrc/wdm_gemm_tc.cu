@@ -31,13 +31,14 @@ constexpr int kBK = 64;                       // bf16 elements per k-block = 128
 constexpr int kABytes = kBM * kBK * 2;        // 16 KiB
 constexpr int kSmemBudget = 196608;           // operand ring bytes (192 KiB)
 constexpr int kThreads = 256;
-constexpr bool kWeightPrefetch = false;  // measured: the extra L2 lookups cost more than the latency they hide
 
 struct TcArgs {
     int m_tiles, n_tiles;
     int M;
-    int kc0, kc1;            // 64-channel chunks per tap taken from source 0 / 1
-    int taps, stride, pad;
+    // K loop = up to 3 segments; segment g reads tensor map g with seg_taps[g] taps x seg_kc[g] 64-channel chunks:
+    //   conv: {main taps};  1x1 over a concat: {src0, src1} one tap each;  conv2 + nin_shortcut: {9-tap main, tails}
+    int nseg, seg_taps[3], seg_kc[3];
+    int stride, pad;
     int Wout, HWout;         // output width, pixels per patch
     int b_batched, tiles_per_batch, a_shared;
     float alpha;
@@ -224,7 +225,7 @@ __device__ __forceinline__ void epilogue_rows(const TcArgs& a, uint32_t tacc, in
 template <int BN, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     using C = Cfg<BN, MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -240,6 +241,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA0);
         ptx::prefetch_tmap(&tmA1);
+        ptx::prefetch_tmap(&tmA2);
         ptx::prefetch_tmap(&tmB);
     }
     if (warp == 1 && lane == 0) {
@@ -264,8 +266,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     wdm_grid_dependency_wait();  // PDL: everything above overlapped the previous kernel's tail
 
     const int num_tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;  // super-tiles of MT m-tiles
-    const int kc_per_tap = a.kc0 + a.kc1;
-    const int kblocks = a.taps * kc_per_tap;
+    int kblocks = 0;
+    for (int g = 0; g < a.nseg; ++g) kblocks += a.seg_taps[g] * a.seg_kc[g];
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -278,44 +280,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const int mt = st * MT + h;
                 const int m0 = (a.a_shared ? mt % a.tiles_per_batch : mt) * kBM;
                 n_img[h] = m0 / a.HWout;
-                cy0[h] = ((m0 - n_img[h] * a.HWout) / a.Wout) * a.stride - a.pad;
+                cy0[h] = ((m0 - n_img[h] * a.HWout) / a.Wout) * a.stride;
             }
             const int bb = a.b_batched ? (st * MT) / a.tiles_per_batch : 0;
-            // Weights stream from DRAM on first touch: run an L2 prefetch kPF k-blocks ahead of the smem ring so the
-            // ring's loads see L2 latency (the ring alone holds only kStages k-blocks in flight).
-            constexpr int kPF = 8;
-            if (kWeightPrefetch && lane == 0 && !a.b_batched) {
-                for (int j = 0; j < kPF && j < kblocks; ++j) ptx::tma_prefetch_2d(&tmB, j * kBK, nt * BN);
-            }
             int kb_lin = 0;
-            for (int tap = 0; tap < a.taps; ++tap) {
-                int dy = a.taps == 9 ? tap / 3 : 0, dx = a.taps == 9 ? tap % 3 : 0;
-                if (a.subpix) dy = (bb >> 1) - 1 + (tap >> 1), dx = (bb & 1) - 1 + (tap & 1);  // bb = output phase
-                const int cx = dx - a.pad;
-                for (int kc = 0; kc < kc_per_tap; ++kc, ++it) {
-                    const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
-                    ptx::mbar_wait(&empty[s], ph ^ 1);
-                    if (lane == 0) {
-                        uint8_t* sa = smem + s * C::kStage;
-                        uint8_t* sb = sa + MT * kABytes;
-                        if (kWeightPrefetch && !a.b_batched && kb_lin + kPF < kblocks) ptx::tma_prefetch_2d(&tmB, (kb_lin + kPF) * kBK, nt * BN);
-                        ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
+            for (int g = 0; g < a.nseg; ++g) {
+                const CUtensorMap* tm = g == 0 ? &tmA0 : (g == 1 ? &tmA1 : &tmA2);
+                const int staps = a.seg_taps[g], skc = a.seg_kc[g];
+                const int pad = staps == 9 ? a.pad : 0;  // 1x1 segments (incl. the shortcut tails) read the centre pixel
+                for (int tap = 0; tap < staps; ++tap) {
+                    int dy = staps == 9 ? tap / 3 : 0, dx = staps == 9 ? tap % 3 : 0;
+                    if (a.subpix) dy = (bb >> 1) - 1 + (tap >> 1), dx = (bb & 1) - 1 + (tap & 1);  // bb = output phase
+                    const int cx = dx - pad;
+                    for (int kc = 0; kc < skc; ++kc, ++it, ++kb_lin) {
+                        const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
+                        ptx::mbar_wait(&empty[s], ph ^ 1);
+                        if (lane == 0) {
+                            uint8_t* sa = smem + s * C::kStage;
+                            uint8_t* sb = sa + MT * kABytes;
+                            ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
 #pragma unroll
-                        for (int h = 0; h < MT; ++h) {
-                            if (kc < a.kc0)
-                                ptx::tma_load_4d(sa + h * kABytes, &tmA0, &full[s], kc * kBK, cx, cy0[h] + dy, n_img[h]);
+                            for (int h = 0; h < MT; ++h)
+                                ptx::tma_load_4d(sa + h * kABytes, tm, &full[s], kc * kBK, cx, cy0[h] + dy - pad, n_img[h]);
+                            if (a.b_batched)
+                                ptx::tma_load_3d(sb, &tmB, &full[s], kb_lin * kBK, nt * BN, bb);
                             else
-                                ptx::tma_load_4d(sa + h * kABytes, &tmA1, &full[s], (kc - a.kc0) * kBK, cx, cy0[h] + dy,
-                                                 n_img[h]);
+                                ptx::tma_load_2d(sb, &tmB, &full[s], kb_lin * kBK, nt * BN);
                         }
-                        const int kcoord = (tap * kc_per_tap + kc) * kBK;
-                        if (a.b_batched)
-                            ptx::tma_load_3d(sb, &tmB, &full[s], kcoord, nt * BN, bb);
-                        else
-                            ptx::tma_load_2d(sb, &tmB, &full[s], kcoord, nt * BN);
+                        __syncwarp();
                     }
-                    __syncwarp();
-                    ++kb_lin;
                 }
             }
         }
@@ -407,7 +400,7 @@ struct Cfg2 {
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     using C = Cfg2<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -425,6 +418,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmA0);
         ptx::prefetch_tmap(&tmA1);
+        ptx::prefetch_tmap(&tmA2);
         ptx::prefetch_tmap(&tmB);
     }
     if (warp == 1 && lane == 0) {
@@ -450,8 +444,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     wdm_grid_dependency_wait();  // PDL: everything above overlapped the previous kernel's tail
 
     const int num_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;  // 256-row super-tiles
-    const int kc_per_tap = a.kc0 + a.kc1;
-    const int kblocks = a.taps * kc_per_tap;
+    int kblocks = 0;
+    for (int g = 0; g < a.nseg; ++g) kblocks += a.seg_taps[g] * a.seg_kc[g];
     const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
 
     if (warp == 0) {
@@ -462,31 +456,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const int mt = st * 2 + (int)rank;
             const int m0 = (a.a_shared ? mt % a.tiles_per_batch : mt) * kBM;
             const int n_img = m0 / a.HWout;
-            const int cy0 = ((m0 - n_img * a.HWout) / a.Wout) * a.stride - a.pad;
+            const int cy0 = ((m0 - n_img * a.HWout) / a.Wout) * a.stride;
             const int bb = a.b_batched ? (st * 2) / a.tiles_per_batch : 0;
             const int nrow = nt * BN + (int)rank * (BN / 2);
-            for (int tap = 0; tap < a.taps; ++tap) {
-                int dy = a.taps == 9 ? tap / 3 : 0, dx = a.taps == 9 ? tap % 3 : 0;
-                if (a.subpix) dy = (bb >> 1) - 1 + (tap >> 1), dx = (bb & 1) - 1 + (tap & 1);  // bb = output phase
-                const int cx = dx - a.pad;
-                for (int kc = 0; kc < kc_per_tap; ++kc, ++it) {
-                    const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
-                    ptx::mbar_wait(&empty[s], ph ^ 1);
-                    if (lane == 0) {
-                        uint8_t* sa = smem + s * C::kStage;
-                        uint8_t* sb = sa + kABytes;
-                        if (leader) ptx::mbar_arrive_expect_tx(&full[s], 2 * C::kStage);  // bytes of BOTH CTAs
-                        if (kc < a.kc0)
-                            ptx::tma2_load_4d(sa, &tmA0, &full[s], kc * kBK, cx, cy0 + dy, n_img);
-                        else
-                            ptx::tma2_load_4d(sa, &tmA1, &full[s], (kc - a.kc0) * kBK, cx, cy0 + dy, n_img);
-                        const int kcoord = (tap * kc_per_tap + kc) * kBK;
-                        if (a.b_batched)
-                            ptx::tma2_load_3d(sb, &tmB, &full[s], kcoord, nrow, bb);
-                        else
-                            ptx::tma2_load_2d(sb, &tmB, &full[s], kcoord, nrow);
+            int kb_lin = 0;
+            for (int g = 0; g < a.nseg; ++g) {
+                const CUtensorMap* tm = g == 0 ? &tmA0 : (g == 1 ? &tmA1 : &tmA2);
+                const int staps = a.seg_taps[g], skc = a.seg_kc[g];
+                const int pad = staps == 9 ? a.pad : 0;
+                for (int tap = 0; tap < staps; ++tap) {
+                    int dy = staps == 9 ? tap / 3 : 0, dx = staps == 9 ? tap % 3 : 0;
+                    if (a.subpix) dy = (bb >> 1) - 1 + (tap >> 1), dx = (bb & 1) - 1 + (tap & 1);  // bb = output phase
+                    const int cx = dx - pad;
+                    for (int kc = 0; kc < skc; ++kc, ++it, ++kb_lin) {
+                        const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
+                        ptx::mbar_wait(&empty[s], ph ^ 1);
+                        if (lane == 0) {
+                            uint8_t* sa = smem + s * C::kStage;
+                            uint8_t* sb = sa + kABytes;
+                            if (leader) ptx::mbar_arrive_expect_tx(&full[s], 2 * C::kStage);  // bytes of BOTH CTAs
+                            ptx::tma2_load_4d(sa, tm, &full[s], kc * kBK, cx, cy0 + dy - pad, n_img);
+                            if (a.b_batched)
+                                ptx::tma2_load_3d(sb, &tmB, &full[s], kb_lin * kBK, nrow, bb);
+                            else
+                                ptx::tma2_load_2d(sb, &tmB, &full[s], kb_lin * kBK, nrow);
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
             }
         }
@@ -589,26 +585,28 @@ int num_sms_tc() {
 }
 
 template <int BN, int MT>
-int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& B, const TcArgs& a, cudaStream_t s) {
+int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& A2, const CUtensorMap& B, const TcArgs& a,
+              cudaStream_t s) {
     using C = Cfg<BN, MT>;
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     const int tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;
     const int grid = tiles < num_sms_tc() ? tiles : num_sms_tc();
-    e = wdm_launch_pdl(gemm_tc_kernel<BN, MT>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, B, a);
+    e = wdm_launch_pdl(gemm_tc_kernel<BN, MT>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, A2, B, a);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     return wdm_launch_status();
 }
 
 template <int BN>
-int launch_pair(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& B, const TcArgs& a, cudaStream_t s) {
+int launch_pair(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& A2, const CUtensorMap& B, const TcArgs& a,
+                cudaStream_t s) {
     using C = Cfg2<BN>;
     cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     const int tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
     const int pairs = num_sms_tc() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    e = wdm_launch_pdl(gemm_tc2_kernel<BN>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, B, a);
+    e = wdm_launch_pdl(gemm_tc2_kernel<BN>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, A2, B, a);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     return wdm_launch_status();
 }
@@ -638,6 +636,13 @@ bool gemm_tc_supported(const GemmParams& p) {
         if (pick_bn(p.N) != 256 && ((p.M / 4 / kBM) % 2)) return false;
     }
     if ((p.C0 % kBK) || (p.C1 % kBK) || p.C0 <= 0) return false;
+    if (p.tail_1x1) {
+        if (!p.C1 || (p.C2 % kBK) || p.stride != 1 || p.ups || p.a_shared || p.b_batch_stride) return false;
+        if (p.K != p.taps * p.C0 + p.C1 + p.C2) return false;
+        if ((p.ld1 % 8) || !wdm_aligned(p.src1, 16) || (p.C2 && ((p.ld2 % 8) || !wdm_aligned(p.src2, 16)))) return false;
+    } else if (p.C1 && p.taps != 1) {
+        return false;  // a channel concat under a 3x3 is K-ordered tap-major: CUDA-core kernel only (unused by the UNet)
+    }
     if (p.taps != 1 && p.taps != 9 && !(p.taps == 4 && p.ups == 2)) return false;
     if (p.stride != 1 && p.stride != 2) return false;
     if (p.taps == 1 && p.stride != 1) return false;
@@ -656,7 +661,7 @@ bool gemm_tc_supported(const GemmParams& p) {
         return false;
     if (p.bias && !wdm_aligned(p.bias, 16)) return false;
     if (p.temb && (!wdm_aligned(p.temb, 16) || (p.temb_ld % 4))) return false;
-    if (p.K != p.taps * (p.C0 + p.C1)) return false;
+    if (!p.tail_1x1 && p.K != p.taps * (p.C0 + p.C1)) return false;
     return true;
 }
 
@@ -688,7 +693,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         pair_enabled && BN == 256 && ((!p.b_batch_stride && !subpix) || tiles_per_batch_h % 2 == 0);
     const int b_box_rows = use_pair ? BN / 2 : BN;
 
-    CUtensorMap A0, A1, B;
+    CUtensorMap A0, A1, A2, B;
     auto make_a = [&](CUtensorMap* m, const void* src, int C, int ld) -> int {
         uint64_t dims[4] = {(uint64_t)C, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)npatch};
         uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)p.Win * ld * 2, (uint64_t)p.Hin * p.Win * ld * 2};
@@ -704,6 +709,12 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         if (r) return r < 0 ? WDM_ERR_UNSUPPORTED : wdm_cuda_error(r);
     } else {
         A1 = A0;
+    }
+    if (p.tail_1x1 && p.C2) {
+        r = make_a(&A2, p.src2, p.C2, p.ld2);
+        if (r) return r < 0 ? WDM_ERR_UNSUPPORTED : wdm_cuda_error(r);
+    } else {
+        A2 = A0;
     }
     if (p.b_batch_stride || subpix) {
         const int nb = subpix ? 4 : p.M / HWout;
@@ -725,8 +736,12 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     a.m_tiles = (p.M + kBM - 1) / kBM;
     a.n_tiles = p.N / BN;
     a.M = p.M;
-    a.kc0 = p.C0 / kBK, a.kc1 = p.C1 / kBK;
-    a.taps = p.taps, a.stride = p.stride, a.pad = p.pad;
+    a.nseg = 1;
+    a.seg_taps[0] = p.taps, a.seg_kc[0] = p.C0 / kBK;
+    a.seg_taps[1] = a.seg_taps[2] = 1, a.seg_kc[1] = a.seg_kc[2] = 0;
+    if (p.C1) a.seg_kc[1] = p.C1 / kBK, a.nseg = 2;              // 1x1 over a concat, or the first shortcut tail
+    if (p.tail_1x1 && p.C2) a.seg_kc[2] = p.C2 / kBK, a.nseg = 3;  // second shortcut tail
+    a.stride = p.stride, a.pad = p.pad;
     a.Wout = Wm, a.HWout = HWout;
     a.b_batched = (p.b_batch_stride || subpix) ? 1 : 0;
     a.tiles_per_batch = tiles_per_batch_h;
@@ -738,12 +753,12 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     a.out_f32 = p.out_dtype == DT_F32;
     a.stats = p.stats_out;
     a.N = p.N;
-    if (use_pair) return launch_pair<256>(A0, A1, B, a, s);
+    if (use_pair) return launch_pair<256>(A0, A1, A2, B, a, s);
     const bool allow2 = !a.b_batched || (a.tiles_per_batch % 2 == 0);
     const int MT = g_force_mt ? (g_force_mt == 2 && allow2 && BN != 64 ? 2 : 1) : pick_mt(a.m_tiles, a.n_tiles, BN, allow2);
-    if (BN == 256) return MT == 2 ? launch_bn<256, 2>(A0, A1, B, a, s) : launch_bn<256, 1>(A0, A1, B, a, s);
-    if (BN == 128) return MT == 2 ? launch_bn<128, 2>(A0, A1, B, a, s) : launch_bn<128, 1>(A0, A1, B, a, s);
-    return launch_bn<64, 1>(A0, A1, B, a, s);
+    if (BN == 256) return MT == 2 ? launch_bn<256, 2>(A0, A1, A2, B, a, s) : launch_bn<256, 1>(A0, A1, A2, B, a, s);
+    if (BN == 128) return MT == 2 ? launch_bn<128, 2>(A0, A1, A2, B, a, s) : launch_bn<128, 1>(A0, A1, A2, B, a, s);
+    return launch_bn<64, 1>(A0, A1, A2, B, a, s);
 }
 
 }  // namespace wdm

@@ -40,6 +40,7 @@ struct ResSpec {
     int Cin = 0, Cout = 0;
     GnSpec norm1, norm2;
     ConvSpec conv1, conv2, nin;
+    ConvSpec conv2f;  // bf16 mode, has_nin: conv2 and nin_shortcut K-concatenated [Cout][9*Cout + Cin], bias = b2 + bnin
     bool has_nin = false;
     int temb_w = -1, temb_b = -1;
     int temb_off = 0;
@@ -324,6 +325,20 @@ int pack_model(wdm_unet* net, const float* flat, cudaStream_t s, size_t* total) 
         pack_gn(r.norm2);
         pack_conv(r.conv2, r.Cout);
         if (r.has_nin) pack_conv(r.nin, r.Cin);
+        if (r.has_nin && dt == DT_BF16) {
+            ConvSpec& f = r.conv2f;
+            f.Cin = r.Cout, f.Cout = r.Cout, f.taps = 9, f.Cin_pad = r.Cout;
+            const long long ldk = 9LL * r.Cout + r.Cin;
+            f.pw = take((size_t)r.Cout * ldk * es);
+            f.pb = reinterpret_cast<float*>(take((size_t)r.Cout * 4));
+            if (fill && st == WDM_OK)
+                st = launch_pack_conv_weight(flat + m.params[r.conv2.w].off, r.Cout, r.Cout, 9, r.Cout, f.pw, dt, ldk, 0, s);
+            if (fill && st == WDM_OK)
+                st = launch_pack_conv_weight(flat + m.params[r.nin.w].off, r.Cout, r.Cin, 1, r.Cin, f.pw, dt, ldk,
+                                             9LL * r.Cout, s);
+            if (fill && st == WDM_OK)
+                st = launch_vec_add(flat + m.params[r.conv2.b].off, flat + m.params[r.nin.b].off, f.pb, r.Cout, s);
+        }
     };
     auto pack_attn = [&](AttnSpec& a) {
         pack_gn(a.norm);
@@ -542,6 +557,35 @@ Act resblock_op(Ctx& c, const Act& x, const Act* x2, const ResSpec& r) {
     Act n2 = gn_op(c, h1, nullptr, r.norm2, 1);
     free_act(c, h1);
     Act out;
+    if (r.has_nin && r.conv2f.pw) {
+        // tensor-core path: x + conv2(h), x = nin(cat[x, x2]), as ONE contraction over K = 9*Cout + Cin
+        GemmParams p;
+        memset(&p, 0, sizeof p);
+        p.src0 = n2.p, p.C0 = n2.C, p.ld0 = n2.C;
+        p.src1 = x.p, p.C1 = x.C, p.ld1 = x.C;
+        if (x2) p.src2 = x2->p, p.C2 = x2->C, p.ld2 = x2->C;
+        p.tail_1x1 = 1;
+        p.Hin = p.Hout = n2.H, p.Win = p.Wout = n2.W;
+        p.taps = 9, p.stride = 1, p.pad = 1;
+        p.B = r.conv2f.pw, p.ldb = 9 * r.Cout + r.Cin, p.b_layout = BL_NK;
+        p.M = c.P * n2.H * n2.W, p.N = r.Cout, p.K = 9 * r.Cout + r.Cin;
+        p.alpha = 1.f, p.bias = r.conv2f.pb;
+        p.ldo = r.Cout;
+        p.a_dtype = p.b_dtype = p.out_dtype = c.net->dt;
+        p.out = reinterpret_cast<void*>(16);
+        if (will_use_tc(c, p)) {
+            out = new_act(c, n2.H, n2.W, r.Cout);
+            p.out = out.p;
+            if ((p.M % 32) == 0 && (n2.H * n2.W) % 32 == 0) {
+                out.stats = reinterpret_cast<float*>(c.ar->alloc((size_t)(p.M / 32) * (p.N / 4) * 2 * sizeof(float)));
+                if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
+                p.stats_out = out.stats;
+            }
+            run_gemm(c, p);
+            free_act(c, n2);
+            return out;
+        }
+    }
     if (r.has_nin) {
         Act sc = conv_op(c, x, x2, r.nin, 1, 0, nullptr, nullptr);
         out = conv_op(c, n2, nullptr, r.conv2, 1, 0, nullptr, &sc, true);
