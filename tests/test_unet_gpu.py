@@ -398,7 +398,7 @@ def test_unet_full_bf16_tc_vs_reference_golden():
     eng.forward(x.to(DEV), torch.from_numpy(g["t"]).to(DEV))
     tc_ms, tc_fl, tc_n, s_ms, s_fl, s_n = eng.profile_read()
     eng.profile(False)
-    assert tc_n >= 80 and tc_fl > 0.95 * (tc_fl + s_fl), (tc_n, s_n, tc_fl, s_fl)
+    assert tc_n >= 70 and tc_fl > 0.95 * (tc_fl + s_fl), (tc_n, s_n, tc_fl, s_fl)
 
 
 def test_unet_full_fp32_vs_reference_golden():
