@@ -178,23 +178,43 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ s0,
     T* o = out + (long long)p * HW * C + c;
     const int px0 = blockIdx.x * pix_per_cta;
     const int px1 = min(HW, px0 + pix_per_cta);
-    constexpr int U = 4;  // independent 16-byte loads in flight per thread
-    for (int px = px0 + lane_pix; px < px1; px += U * ppi) {
-        float v[U][V];
+    // All of this thread's loads are issued before the first use (raw 16-byte registers, converted on the fly), so one
+    // CTA pass keeps U x 16 B per thread in flight; the launcher sizes CTAs to exactly one such pass.
+    constexpr int U = 8;
+    constexpr int R = sizeof(T) * V / 16;  // 16-byte registers per vector (1 for bf16, 2 for fp32)
+    uint4 raw[U][R];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (px + u * ppi < px1) Vec<T, V>::load(base + (long long)(px + u * ppi) * ld, v[u]);
+    for (int u = 0; u < U; ++u) {
+        const int px = px0 + lane_pix + u * ppi;
+        if (px < px1) {
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (px + u * ppi < px1) {
+            for (int r = 0; r < R; ++r) raw[u][r] = __ldg(reinterpret_cast<const uint4*>(base + (long long)px * ld) + r);
+        }
+    }
 #pragma unroll
-                for (int i = 0; i < V; ++i) {
-                    float y = fmaf(v[u][i], a[i], b[i]);
-                    if (kSilu) y = kPrecise ? silu_precise(y) : wdm_silu(y);
-                    v[u][i] = y;
+    for (int u = 0; u < U; ++u) {
+        const int px = px0 + lane_pix + u * ppi;
+        if (px < px1) {
+            float v[V];
+            if (sizeof(T) == 2) {
+                const uint32_t w[4] = {raw[u][0].x, raw[u][0].y, raw[u][0].z, raw[u][0].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[2 * i] = __uint_as_float(w[i] << 16), v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    v[4 * r] = __uint_as_float(raw[u][r].x), v[4 * r + 1] = __uint_as_float(raw[u][r].y);
+                    v[4 * r + 2] = __uint_as_float(raw[u][r].z), v[4 * r + 3] = __uint_as_float(raw[u][r].w);
                 }
-                Vec<T, V>::store(o + (long long)(px + u * ppi) * C, v[u]);
             }
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                float y = fmaf(v[i], a[i], b[i]);
+                if (kSilu) y = kPrecise ? silu_precise(y) : wdm_silu(y);
+                v[i] = y;
+            }
+            Vec<T, V>::store(o + (long long)px * C, v);
+        }
     }
 }
 
@@ -540,9 +560,7 @@ int launch_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtyp
     GnGeom g;
     if (!gn_geom_apply(C0, C1, &g)) return WDM_ERR_BAD_SHAPE;
     const int ppi = g.threads / g.nvec;
-    // >= ~4 CTAs per SM when the tensor allows it, but at least 8 pixels per thread-row to amortise the prologue
-    int pix_per_cta = ppi * 32;
-    while (pix_per_cta > ppi * 8 && (long long)P * ((HW + pix_per_cta - 1) / pix_per_cta) < 4 * 148) pix_per_cta >>= 1;
+    int pix_per_cta = ppi * 8;  // one pass of U = 8 vectors per thread (see gn_apply_kernel)
     if (pix_per_cta > HW) pix_per_cta = HW;
     dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, P);
 #define WDM_GN_APPLY(T, SILU, PREC)                                                                               \
