@@ -296,8 +296,10 @@ __global__ void upsample2x_kernel(const T* __restrict__ src, int P, int H, int W
 
 // ---------------------------------------------------------------------------------------------- softmax
 // one warp per row, L <= 1024, L % 32 == 0
+// seg > 0: block-diagonal attention over groups of L/seg patches packed in one row (the 8x8 mid-block runs two
+// 64-token patches per 128-row tile): row r only attends to columns [seg*((r/seg) % (L/seg)), +seg); the others get 0.
 template <typename TO>
-__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, long long rows, int L,
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, long long rows, int L, int seg,
                                                            TO* __restrict__ out) {
     wdm_grid_launch_dependents();
     wdm_grid_dependency_wait();
@@ -307,11 +309,13 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     const float* s = S + row * L;
     float v[32];
     const int n = L >> 5;
+    const int c0 = seg > 0 ? (int)((row / seg) % (L / seg)) * seg : 0, c1 = seg > 0 ? c0 + seg : L;
     float mx = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
         if (i < n) {
-            v[i] = s[i * 32 + lane];
+            const int col = i * 32 + lane;
+            v[i] = (col >= c0 && col < c1) ? s[col] : -INFINITY;
             mx = fmaxf(mx, v[i]);
         }
 #pragma unroll
@@ -599,13 +603,13 @@ int launch_upsample2x(const void* src, int dtype, int P, int H, int W, int C, vo
     return wdm_launch_status();
 }
 
-int launch_softmax_rows(const float* S, int rows, int L, void* out, int out_dtype, cudaStream_t s) {
-    if (L % 32 || L > 1024) return WDM_ERR_BAD_SHAPE;
+int launch_softmax_rows(const float* S, int rows, int L, void* out, int out_dtype, cudaStream_t s, int seg) {
+    if (L % 32 || L > 1024 || (seg > 0 && (L % seg))) return WDM_ERR_BAD_SHAPE;
     const unsigned grid = (unsigned)((rows + 7) / 8);
     if (out_dtype == DT_F32)
-        wdm_launch_pdl(softmax_rows_kernel<float>, dim3(grid), dim3(256), 0, s, S, (long long)rows, L, reinterpret_cast<float*>(out));
+        wdm_launch_pdl(softmax_rows_kernel<float>, dim3(grid), dim3(256), 0, s, S, (long long)rows, L, seg, reinterpret_cast<float*>(out));
     else
-        wdm_launch_pdl(softmax_rows_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, S, (long long)rows, L,
+        wdm_launch_pdl(softmax_rows_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, S, (long long)rows, L, seg,
                        reinterpret_cast<__nv_bfloat16*>(out));
     return wdm_launch_status();
 }

@@ -49,7 +49,7 @@ int launch_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtyp
 // nearest x2 upsample NHWC (bf16 path only; the fp32 path folds it into the conv addressing)
 int launch_upsample2x(const void* src, int dtype, int P, int H, int W, int C, void* out, cudaStream_t stream);
 // row softmax: S fp32 [rows][L] -> probabilities in out_dtype [rows][L]
-int launch_softmax_rows(const float* S, int rows, int L, void* out, int out_dtype, cudaStream_t stream);
+int launch_softmax_rows(const float* S, int rows, int L, void* out, int out_dtype, cudaStream_t stream, int seg = 0);
 
 // timestep path (models/unet.py:10-28,354-357,125): temb[T][4ch] then all per-block projections
 //   out[T][total] = concat_b( Linear_b(silu(temb)) + conv1_b.bias )

@@ -254,83 +254,97 @@ int launch_t(const GemmParams& p, cudaStream_t s) {
 }
 
 // ---- conv_out: Cout <= 4, NHWC in, NCHW fp32 out -------------------------------------------------------
-// One CTA per (patch, output row): the three input rows are staged in shared memory once (coalesced 16-byte loads,
-// zero rows/columns for the padding), weights [Cout][9][C] in shared memory as fp32. Thread = (4 adjacent pixels,
-// one 8-channel slice); the C/8 slices of a pixel group sit in adjacent lanes and are shuffle-reduced.
+// One CTA per (patch, strip of kStripRows output rows): a rolling window of three input rows lives in shared memory
+// (each input row is loaded once per strip, coalesced 16-byte loads, zero rows/columns for the padding), weights
+// [Cout][9][C] in shared memory as fp32. Thread = (4 adjacent pixels, one 8-channel slice); the C/8 slices of a pixel
+// group sit in adjacent lanes and are shuffle-reduced.
+constexpr int kStripRows = 8;
+
 template <typename T>
 __global__ void __launch_bounds__(256, 2) conv_small_cout_kernel(const T* __restrict__ src, int P, int H, int W, int C,
-                                                              const float* __restrict__ w,
-                                                              const float* __restrict__ bias, int Cout,
-                                                              float* __restrict__ out) {
+                                                                 const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, int Cout,
+                                                                 float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_cs[];
-    const int y = blockIdx.x, p = blockIdx.y;
+    const int y0 = blockIdx.x * kStripRows, p = blockIdx.y;
     const int Wp = W + 2;
-    T* rows = reinterpret_cast<T*>(smem_cs);                                    // [3][W+2][C]
+    T* rows = reinterpret_cast<T*>(smem_cs);                                         // ring [3][W+2][C]
     float* sw = reinterpret_cast<float*>(smem_cs + (size_t)3 * Wp * C * sizeof(T));  // [Cout][9][C]
     for (int i = threadIdx.x; i < Cout * 9 * C; i += blockDim.x) sw[i] = w[i];
     constexpr int VE = 16 / sizeof(T);  // elements per 16-byte vector
     const int vec_per_row = Wp * C / VE;
-    for (int i = threadIdx.x; i < 3 * vec_per_row; i += blockDim.x) {
-        const int r = i / vec_per_row, v = i - r * vec_per_row;
-        const int px = (v * VE) / C - 1, c = (v * VE) % C;
-        const int iy = y + r - 1;
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (iy >= 0 && iy < H && px >= 0 && px < W)
-            q = __ldg(reinterpret_cast<const uint4*>(src + (((long long)p * H + iy) * W + px) * C + c));
-        reinterpret_cast<uint4*>(rows)[i] = q;
-    }
-    __syncthreads();
-    const int nslice = C / 8;                 // 16 for C = 128 (must divide 32)
+    auto load_row = [&](int iy) {  // input row iy -> ring slot (iy + 3) % 3
+        uint4* dst = reinterpret_cast<uint4*>(rows + (size_t)((iy + 3) % 3) * Wp * C);
+        for (int v = threadIdx.x; v < vec_per_row; v += blockDim.x) {
+            const int px = (v * VE) / C - 1, c = (v * VE) % C;
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (iy >= 0 && iy < H && px >= 0 && px < W)
+                q = __ldg(reinterpret_cast<const uint4*>(src + (((long long)p * H + iy) * W + px) * C + c));
+            dst[v] = q;
+        }
+    };
+    load_row(y0 - 1);
+    load_row(y0);
+    const int nslice = C / 8;  // 16 for C = 128 (must divide 32)
     const int s = threadIdx.x % nslice;
     const int groups_per_pass = blockDim.x / nslice;
-    for (int pg = threadIdx.x / nslice; pg * 4 < W; pg += groups_per_pass) {
-        float acc[4][4];
+    const int yend = min(H, y0 + kStripRows);
+    for (int y = y0; y < yend; ++y) {
+        load_row(y + 1);
+        __syncthreads();
+        for (int pg = threadIdx.x / nslice; pg * 4 < W; pg += groups_per_pass) {
+            float acc[4][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int o = 0; o < 4; ++o) acc[a][o] = 0.f;
+                for (int o = 0; o < 4; ++o) acc[a][o] = 0.f;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap % 3;
-            float wv[4][8];
+            for (int tap = 0; tap < 9; ++tap) {
+                const int dy = tap / 3, dx = tap % 3;
+                const T* rrow = rows + (size_t)((y + dy - 1 + 3) % 3) * Wp * C;
+                float wv[4][8];
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                if (o < Cout) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * C + s * 8);
-                    const float4 w1 = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * C + s * 8 + 4);
-                    wv[o][0] = w0.x, wv[o][1] = w0.y, wv[o][2] = w0.z, wv[o][3] = w0.w;
-                    wv[o][4] = w1.x, wv[o][5] = w1.y, wv[o][6] = w1.z, wv[o][7] = w1.w;
+                for (int o = 0; o < 4; ++o) {
+                    if (o < Cout) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * C + s * 8);
+                        const float4 w1 = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * C + s * 8 + 4);
+                        wv[o][0] = w0.x, wv[o][1] = w0.y, wv[o][2] = w0.z, wv[o][3] = w0.w;
+                        wv[o][4] = w1.x, wv[o][5] = w1.y, wv[o][6] = w1.z, wv[o][7] = w1.w;
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int px = pg * 4 + a + dx;  // index in the padded row (pixel x + dx - 1 + 1)
+                    float v[8];
+                    lds8(rrow + (size_t)px * C + s * 8, v);
+#pragma unroll
+                    for (int o = 0; o < 4; ++o)
+                        if (o < Cout) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) acc[a][o] = fmaf(v[i], wv[o][i], acc[a][o]);
+                        }
                 }
             }
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const int px = pg * 4 + a + dx;  // index in the padded row (pixel x + dx - 1 + 1)
-                float v[8];
-                lds8(rows + ((size_t)dy * Wp + px) * C + s * 8, v);
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int o = 0; o < 4; ++o)
                     if (o < Cout) {
+                        for (int off = nslice >> 1; off; off >>= 1)
+                            acc[a][o] += __shfl_xor_sync(0xffffffffu, acc[a][o], off);
+                    }
+            if (s == 0) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[a][o] = fmaf(v[i], wv[o][i], acc[a][o]);
+                for (int o = 0; o < 4; ++o)
+                    if (o < Cout) {
+                        float* d = out + (((long long)p * Cout + o) * H + y) * W + pg * 4;
+                        const float b = bias ? bias[o] : 0.f;
+                        *reinterpret_cast<float4*>(d) =
+                            make_float4(acc[0][o] + b, acc[1][o] + b, acc[2][o] + b, acc[3][o] + b);
                     }
             }
         }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int o = 0; o < 4; ++o)
-                if (o < Cout) {
-                    for (int off = nslice >> 1; off; off >>= 1) acc[a][o] += __shfl_xor_sync(0xffffffffu, acc[a][o], off);
-                }
-        if (s == 0) {
-#pragma unroll
-            for (int o = 0; o < 4; ++o)
-                if (o < Cout) {
-                    float* d = out + (((long long)p * Cout + o) * H + y) * W + pg * 4;
-                    const float b = bias ? bias[o] : 0.f;
-                    *reinterpret_cast<float4*>(d) = make_float4(acc[0][o] + b, acc[1][o] + b, acc[2][o] + b, acc[3][o] + b);
-                }
-        }
+        __syncthreads();  // the next iteration overwrites the slot of row y - 1
     }
 }
 
@@ -361,7 +375,7 @@ int launch_conv_small_cout(const void* src, int dtype, int P, int H, int W, int 
     const size_t es = dtype == DT_F32 ? 4 : 2;
     const size_t smem = (size_t)3 * (W + 2) * C * es + (size_t)Cout * 9 * C * sizeof(float);
     if (smem > 200 * 1024) return WDM_ERR_BAD_SHAPE;
-    dim3 grid(H, P);
+    dim3 grid((H + kStripRows - 1) / kStripRows, P);
     if (dtype == DT_F32) {
         cudaFuncSetAttribute(conv_small_cout_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         conv_small_cout_kernel<float><<<grid, 256, smem, s>>>(reinterpret_cast<const float*>(src), P, H, W, C, w, bias,

@@ -605,8 +605,10 @@ Act resblock_op(Ctx& c, const Act& x, const Act* x2, const ResSpec& r) {
 //   Pm  = softmax(S)                          the softmax sum to one)
 //   O   = Pm vT^T + b_v          [P*L][C]
 //   out = O Wproj^T + b + x
-Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a) {
-    const int C = a.C, L = x.H * x.W, P = c.P;
+Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a, int G) {
+    // G patches share one 128-row tile when a patch has fewer than 128 tokens (the 8x8 mid block: G = 2): the matmuls run
+    // on groups of G*L rows and the softmax is block-diagonal (cross-patch scores are masked to zero probability).
+    const int C = a.C, L = x.H * x.W, P = c.P, Lg = G * L, Hg = G * x.H;
     const size_t es = 2;
     Act n = gn_op(c, x, nullptr, a.norm, 0);
     GemmParams p;
@@ -623,29 +625,29 @@ Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a) {
     memset(&p, 0, sizeof p);
     p.src0 = (char*)a.qkv.pw + (size_t)2 * C * C * es, p.C0 = C, p.ld0 = C, p.a_shared = 1;
     p.Hin = p.Hout = C / 128, p.Win = p.Wout = 128, p.taps = 1, p.stride = 1;
-    p.B = n.p, p.ldb = C, p.b_batch_stride = (long long)L * C, p.b_layout = BL_NK;
-    p.M = P * C, p.N = L, p.K = C, p.alpha = 1.f;
-    p.out = vT, p.ldo = L, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
+    p.B = n.p, p.ldb = C, p.b_batch_stride = (long long)Lg * C, p.b_layout = BL_NK;
+    p.M = (P / G) * C, p.N = Lg, p.K = C, p.alpha = 1.f;
+    p.out = vT, p.ldo = Lg, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
     run_gemm(c, p);
     free_act(c, n);
     // S
-    float* S = reinterpret_cast<float*>(c.ar->alloc((size_t)P * L * L * 4));
-    void* Pm = c.ar->alloc((size_t)P * L * L * es);
+    float* S = reinterpret_cast<float*>(c.ar->alloc((size_t)P * L * Lg * 4));
+    void* Pm = c.ar->alloc((size_t)P * L * Lg * es);
     if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
     memset(&p, 0, sizeof p);
-    p.src0 = qk.p, p.C0 = C, p.ld0 = 2 * C, p.Hin = p.Hout = x.H, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
-    p.B = (char*)qk.p + (size_t)C * es, p.b_batch_stride = (long long)L * 2 * C, p.ldb = 2 * C, p.b_layout = BL_NK;
-    p.M = P * L, p.N = L, p.K = C, p.alpha = (float)(1.0 / sqrt((double)C));
-    p.out = S, p.ldo = L, p.a_dtype = p.b_dtype = DT_BF16, p.out_dtype = DT_F32;
+    p.src0 = qk.p, p.C0 = C, p.ld0 = 2 * C, p.Hin = p.Hout = Hg, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
+    p.B = (char*)qk.p + (size_t)C * es, p.b_batch_stride = (long long)Lg * 2 * C, p.ldb = 2 * C, p.b_layout = BL_NK;
+    p.M = P * L, p.N = Lg, p.K = C, p.alpha = (float)(1.0 / sqrt((double)C));
+    p.out = S, p.ldo = Lg, p.a_dtype = p.b_dtype = DT_BF16, p.out_dtype = DT_F32;
     run_gemm(c, p);
-    if (!c.dry() && c.st == WDM_OK) c.fail(launch_softmax_rows(S, P * L, L, Pm, DT_BF16, c.s));
+    if (!c.dry() && c.st == WDM_OK) c.fail(launch_softmax_rows(S, P * L, Lg, Pm, DT_BF16, c.s, G > 1 ? L : 0));
     free_act(c, qk);
     // O
     Act O = new_act(c, x.H, x.W, C);
     memset(&p, 0, sizeof p);
-    p.src0 = Pm, p.C0 = L, p.ld0 = L, p.Hin = p.Hout = x.H, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
-    p.B = vT, p.b_batch_stride = (long long)C * L, p.ldb = L, p.b_layout = BL_NK;
-    p.M = P * L, p.N = C, p.K = L, p.alpha = 1.f, p.bias = a.qkv.pb + 2 * C;
+    p.src0 = Pm, p.C0 = Lg, p.ld0 = Lg, p.Hin = p.Hout = Hg, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
+    p.B = vT, p.b_batch_stride = (long long)C * Lg, p.ldb = Lg, p.b_layout = BL_NK;
+    p.M = P * L, p.N = C, p.K = Lg, p.alpha = 1.f, p.bias = a.qkv.pb + 2 * C;
     p.out = O.p, p.ldo = C, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
     run_gemm(c, p);
     c.ar->free(S);
@@ -660,8 +662,10 @@ Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a) {
 Act attn_op(Ctx& c, const Act& x, const AttnSpec& a) {
     const int dt = c.net->dt;
     const int C = a.C, L = x.H * x.W, P = c.P;
-    if (dt == DT_BF16 && !(c.net->flags & WDM_ENGINE_NO_TC) && (L % 128) == 0 && (C % 128) == 0 && (L % 64) == 0)
-        return attn_op_tc(c, x, a);
+    if (dt == DT_BF16 && !(c.net->flags & WDM_ENGINE_NO_TC) && (C % 128) == 0) {
+        if ((L % 128) == 0) return attn_op_tc(c, x, a, 1);
+        if (L == 64 && (P % 2) == 0) return attn_op_tc(c, x, a, 2);
+    }
     Act n = gn_op(c, x, nullptr, a.norm, 0);
     Act qkv = conv_op(c, n, nullptr, a.qkv, 1, 0, nullptr, nullptr);  // [P*L][3C]
     free_act(c, n);
