@@ -178,6 +178,24 @@ def main():
     np.savez(os.path.join(OUT, "sandwich_full.npz"), seed=61, steps=10, latent_m5=lat.numpy(),
              out_crop=out[:, :, 96:160, 96:160].numpy(), out_mean=np.float64(out.double().mean()),
              psnr=np.float32(psnr), xs_last=xs[-1].numpy())
+    # ---------------------------------------------------------------- overlapping-patch sampling at 512x512 (config #5 shape)
+    # wavelet domain 128x128, 64x64 patches, grid_r = 16 -> 5x5 = 25 patches per image, 5 DDIM steps (of the 100-step
+    # schedule's spacing this is coarser, the arithmetic is the same).
+    g = torch.Generator().manual_seed(65)
+    xc5 = torch.randn(1, 48, 128, 128, generator=g)
+    xo5 = torch.randn(1, 45, 128, 128, generator=g)
+    xn5 = torch.randn(1, 3, 128, 128, generator=g)
+    hl, wl = ref_ddm.DenoisingDiffusion_Wavelet.overlapping_grid_indices(stubF, xc5, output_size=64, r=16)
+    corners5 = [(i, j) for i in hl for j in wl]
+    assert len(corners5) == 25
+    seq5 = range(0, 1000, 200)
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        xs5, x0p5 = ref_ddm.DenoisingDiffusion_Wavelet.generalized_steps_overlapping(
+            stubF, xn5, xc5, seq5, netF, betas, eta=0., corners=corners5, p_size=64, x_other=xo5, use_other=True)
+    np.savez(os.path.join(OUT, "patched_full.npz"), seed=65, x0_first=x0p5[0].numpy(), x0_last=x0p5[-1].numpy(),
+             xs_last=xs5[-1].numpy(), ncorners=len(corners5), steps=len(x0p5))
+    print("patched_full.npz ok; latent range", float(x0p5[-1].min()), float(x0p5[-1].max()))
+
     print("sandwich_full.npz ok; psnr", float(psnr), "latent range", float(lat.min()), float(lat.max()))
 
 

@@ -158,3 +158,68 @@ def test_reference_api_surface(tmp_path):
     assert diffusion.overlapping_grid_indices(torch.zeros(1, 48, 120, 180), 64, 16) == \
         ([0, 16, 32, 48, 56], [0, 16, 32, 48, 64, 80, 96, 112, 116])
     assert hasattr(diffusion.model, "module") and len(diffusion.model.module.state_dict()) == 332
+
+
+def test_patched_512_fp32_and_bf16_vs_reference_golden(tmp_path):
+    """Config #5 shape: 128x128 wavelet domain, 25 overlapping 64x64 patches per image, against the reference's own
+    generalized_steps_overlapping (golden). fp32 engine: tight; bf16 tensor-core engine: relative L2."""
+    g = golden("patched_full.npz")
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    xc = torch.randn(1, 48, 128, 128, generator=gen)
+    xo = torch.randn(1, 45, 128, 128, generator=gen)
+    xn = torch.randn(1, 3, 128, 128, generator=gen)
+    cfg = O.default_config()
+    sd = O.init_state_dict(cfg, seed=61)
+    hl, wl = O.overlapping_grid_indices(128, 128, 64, 16)
+    corners = [(i, j) for i in hl for j in wl]
+    assert len(corners) == int(g["ncorners"]) == 25
+    betas = O.beta_schedule(cfg)
+    seq = list(range(0, 1000, 200))
+    ref_first, ref_last = torch.from_numpy(g["x0_first"]), torch.from_numpy(g["x0_last"])
+    eng = engine.UNetEngine(cfg, sd, DEV, precision="fp32", max_patches=16)      # 25 patches -> chunks 16 + 9
+    xs, x0 = DdimSampler(eng).sample(xn, xc, xo, seq, betas, corners, 64)
+    assert (x0[0].cpu() - ref_first).abs().max().item() <= 1e-4 * ref_first.abs().max().item()
+    assert (x0[-1].cpu() - ref_last).abs().max().item() <= 2e-4 * ref_last.abs().max().item()
+    assert (xs[-1].cpu() - torch.from_numpy(g["xs_last"])).abs().max().item() <= 2e-4 * ref_last.abs().max().item()
+    del eng
+    eng = engine.UNetEngine(cfg, sd, DEV, precision="bf16", max_patches=64)
+    xs, x0 = DdimSampler(eng).sample(xn, xc, xo, seq, betas, corners, 64)
+    rel = ((x0[-1].cpu() - ref_last).norm() / ref_last.norm()).item()
+    assert rel <= 5e-2, rel
+
+
+def test_sandwich_bf16_psnr_gate(tmp_path):
+    """Throughput mode (bf16 tcgen05): PSNR of the restored image within 0.01 dB of the reference run."""
+    g = golden("sandwich_full.npz")
+    diffusion, restorer, cfg = _make_diffusion(str(tmp_path), "bf16", int(g["steps"]))
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    ximg = torch.rand(1, 6, 256, 256, generator=gen)
+    noise = torch.randn(1, 3, 64, 64, generator=gen)
+    x_gt = diffusion.wavelet_dec(2 * ximg[:, 3:].contiguous().to(DEV) - 1.0)
+    res = restorer.restore_batch(ximg, r=16, noise=noise.to(DEV), x_other=x_gt[:, 3:].contiguous())
+    out = res["output"].cpu()
+    psnr = O.torch_psnr(ximg[:, 3:], out).item()
+    assert abs(psnr - float(g["psnr"])) < 0.01, (psnr, float(g["psnr"]))
+    lat_ref = torch.from_numpy(g["latent_m5"])
+    rel = ((res["latent"].cpu() - lat_ref).norm() / lat_ref.norm()).item()
+    assert rel < 5e-2, rel
+
+
+def test_restore_with_loader_writes_images_and_matches_restore_batch(tmp_path, capsys):
+    """DiffusiveRestoration.restore (restoration.py:63-168) end to end with the loader contract (x, id, total): HFRM
+    branch, x0_preds[-5], PNG side effects and PSNR prints."""
+    diffusion, restorer, cfg = _make_diffusion(str(tmp_path), "fp32", 5)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 6, 256, 256, generator=gen)
+    loader = [(x, "img7", x[:, :3])]
+    torch.manual_seed(11)
+    restorer.restore(loader, validation="raindrop", r=16)
+    out_dir = os.path.join(str(tmp_path), cfg.data.dataset, "raindrop")
+    for name in ("img7_output.png", "img7_cond.png", "img7_gt.png", "img7_all_wdnet.png", "img7_lrdiff_hrgt.png"):
+        assert os.path.isfile(os.path.join(out_dir, name)), name
+    printed = capsys.readouterr().out
+    assert "psnr this" in printed and "psnr all torch" in printed
+    torch.manual_seed(11)
+    res = restorer.restore_batch(x, r=16, want_variants=True)
+    assert res["output"].shape == (1, 3, 256, 256) and float(res["output"].min()) >= 0.0 and float(res["output"].max()) <= 1.0
+    assert set(res) >= {"output", "cond", "latent", "lrdiff_hrgt", "lrgt_hrwdnet", "lrgt_hrcond", "all_wdnet"}
