@@ -180,6 +180,13 @@ typedef struct wdm_gemm_params {
     int tail_1x1;
     const void* src2;
     int C2, ld2;
+    /* tensor-core path only, N == one tile (64/128/256): the epilogue applies a row softmax to alpha*acc and stores the
+     * probabilities (bf16) instead of the scores (models/unet.py:180-182). softmax_seg > 0: block-diagonal, row r only
+     * attends to columns [seg*((r/seg) % (N/seg)), +seg), the rest get probability 0. */
+    int fuse_softmax, softmax_seg;
+    /* tensor-core path only: > 0 = store only the first `out_nchw_valid` (<= 32) output columns, as fp32 NCHW planes
+     * out[(patch*valid + n)*Hout*Wout + pixel] (conv_out with Cout = 3 zero-padded to a 64-wide N tile). */
+    int out_nchw_valid;
 } wdm_gemm_params;
 #define WDM_GEMM_IMPL_SIMT 0
 #define WDM_GEMM_IMPL_TC 1

@@ -28,7 +28,8 @@ class GemmParams(ctypes.Structure):
         [("alpha", ctypes.c_float), ("bias", ctypes.c_void_p), ("temb", ctypes.c_void_p), ("temb_rows", ctypes.c_int),
          ("temb_ld", ctypes.c_int), ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int), ("out", ctypes.c_void_p)] + \
         [(n, ctypes.c_int) for n in ("ldo", "a_dtype", "b_dtype", "out_dtype")] + [("stats_out", ctypes.c_void_p), ("a_shared", ctypes.c_int), ("tail_1x1", ctypes.c_int),
-                                                                                ("src2", ctypes.c_void_p), ("C2", ctypes.c_int), ("ld2", ctypes.c_int)]
+                                                                                ("src2", ctypes.c_void_p), ("C2", ctypes.c_int), ("ld2", ctypes.c_int),
+                                                                                ("fuse_softmax", ctypes.c_int), ("softmax_seg", ctypes.c_int), ("out_nchw_valid", ctypes.c_int)]
 
 
 def run_conv(x, x2, w, bias, stride, ups, temb, residual, dtype, impl, want_stats=False):

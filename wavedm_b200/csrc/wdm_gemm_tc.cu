@@ -29,7 +29,10 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kBK = 64;                       // bf16 elements per k-block = 128 bytes = one swizzle span
 constexpr int kABytes = kBM * kBK * 2;        // 16 KiB
-constexpr int kSmemBudget = 196608;           // operand ring bytes (192 KiB)
+#ifndef WDM_SMEM_BUDGET
+#define WDM_SMEM_BUDGET 196608
+#endif
+constexpr int kSmemBudget = WDM_SMEM_BUDGET;  // operand ring bytes (192 KiB)
 constexpr int kThreads = 256;
 
 struct TcArgs {
@@ -53,6 +56,8 @@ struct TcArgs {
     float* stats;   // GroupNorm side-car [M/32][N/4][2] or null
     int N;
     int subpix;     // nearest-x2-upsample + 3x3 conv as 4 output-phase 2x2 convs (m-tiles are phase-major)
+    int softmax, softmax_seg;  // epilogue = row softmax of alpha*acc over the (single) N tile, bf16 probabilities out
+    int nchw_valid;            // > 0: fp32 NCHW output of the first nchw_valid columns only
 };
 
 // K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1).
@@ -108,6 +113,7 @@ __device__ __forceinline__ void epilogue_rows(const TcArgs& a, uint32_t tacc, in
             }
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
+                if (a.nchw_valid && ch > 0) break;  // only columns [0, 32) carry real output channels
                 uint32_t r[32];
                 uint4 res_cur[4];
                 if (res16) {
@@ -139,7 +145,13 @@ __device__ __forceinline__ void epilogue_rows(const TcArgs& a, uint32_t tacc, in
                             v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
                         }
                     }
-                    if (a.out_f32) {
+                    if (a.nchw_valid) {
+                        const long long patch = m / a.HWout, pix = m - patch * a.HWout;
+                        float* op = reinterpret_cast<float*>(a.out) + patch * a.nchw_valid * a.HWout + pix;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < a.nchw_valid) op[(long long)j * a.HWout] = v[j];
+                    } else if (a.out_f32) {
                         if (a.residual) {
                             const float* rp = reinterpret_cast<const float*>(a.residual) + m * a.ldr + n;
 #pragma unroll
@@ -220,6 +232,68 @@ __device__ __forceinline__ void epilogue_rows(const TcArgs& a, uint32_t tacc, in
                         a.stats[(rg * (a.N >> 2) + ((nt * BN + ch * 32) >> 2)) * 2 + (lane >> 1)] = s1;
                 }
             }
+}
+
+// Attention-score epilogue: the whole key axis of a query row sits in this thread's TMEM lane (N == BN), so the row
+// softmax (models/unet.py:180-182) is three passes over TMEM: max, sum of exp, normalised bf16 store. Scores never
+// touch HBM.
+template <int BN>
+__device__ __forceinline__ void epilogue_softmax(const TcArgs& a, uint32_t tacc, int mt, int row) {
+    const long long m = (long long)mt * kBM + row;
+    const bool valid = m < a.M;
+    const int seg = a.softmax_seg;
+    const int c0 = seg > 0 ? (int)((m / seg) % (BN / seg)) * seg : 0, c1 = seg > 0 ? c0 + seg : BN;
+    const float sc = a.alpha * 1.4426950408889634f;  // exp(x) = exp2(x * log2 e)
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tacc + ch * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = ch * 32 + j;
+            if (col >= c0 && col < c1) mx = fmaxf(mx, __uint_as_float(r[j]) * sc);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tacc + ch * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = ch * 32 + j;
+            if (col >= c0 && col < c1) sum += exp2f(fmaf(__uint_as_float(r[j]), sc, -mx));
+        }
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tacc + ch * 32, r);
+        ptx::tmem_ld_wait();
+        if (valid) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = ch * 32 + j;
+                v[j] = (col >= c0 && col < c1) ? exp2f(fmaf(__uint_as_float(r[j]), sc, -mx)) * inv : 0.f;
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + m * a.ldo + ch * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 t = __floats2bfloat162_rn(v[q * 8 + 2 * i], v[q * 8 + 2 * i + 1]);
+                    w[i] = *reinterpret_cast<uint32_t*>(&t);
+                }
+                op[q] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
 }
 
 template <int BN, int MT>
@@ -367,7 +441,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll 1
             for (int hh = 0; hh < MT; ++hh) {
             const int mt = st * MT + hh;
-            epilogue_rows<BN>(a, tmem_base + ((uint32_t)(ew * 32) << 16) + (as * MT + hh) * BN, mt, nt, ew, lane, row);
+            if (a.softmax)
+                epilogue_softmax<BN>(a, tmem_base + ((uint32_t)(ew * 32) << 16) + (as * MT + hh) * BN, mt, row);
+            else
+                epilogue_rows<BN>(a, tmem_base + ((uint32_t)(ew * 32) << 16) + (as * MT + hh) * BN, mt, nt, ew, lane, row);
             }  // hh
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty[as]);
@@ -532,7 +609,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             }
             ptx::mbar_wait(&tfull[as], aph);
             ptx::tc_fence_after();
-            epilogue_rows<BN>(a, tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN, mt, nt, ew, lane, row);
+            if (a.softmax)
+                epilogue_softmax<BN>(a, tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN, mt, row);
+            else
+                epilogue_rows<BN>(a, tmem_base + ((uint32_t)(ew * 32) << 16) + as * BN, mt, nt, ew, lane, row);
             ptx::tc_fence_before();
             ptx::mbar_arrive_cluster(&tempty[as], 0);
         }
@@ -613,7 +693,7 @@ int launch_pair(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap&
 
 // Operand bytes a CTA pulls through L2 for the whole problem under (BN, MT): waves x bytes per k-block.
 int pick_mt(int m_tiles, int n_tiles, int BN, bool allow2) {
-    if (!allow2 || BN != 128) return 1;  // (256, 2) has a single TMEM buffer: no epilogue overlap, measured slower
+    if (!allow2 || BN == 256) return 1;  // (256, 2) has a single TMEM buffer: no epilogue overlap, measured slower
     const int sms = num_sms_tc();
     auto cost = [&](int mt) {
         const long long tiles = (long long)((m_tiles + mt - 1) / mt) * n_tiles;
@@ -655,6 +735,15 @@ bool gemm_tc_supported(const GemmParams& p) {
         if (p.b_batch_stride % 8) return false;
     }
     if (p.a_shared && (!p.b_batch_stride || p.temb || p.taps != 1)) return false;
+    if (p.out_nchw_valid) {
+        if (p.out_nchw_valid < 0 || p.out_nchw_valid > 4 || p.out_dtype != DT_F32 || p.residual || p.stats_out || p.temb ||
+            p.fuse_softmax || p.ups || p.b_batch_stride)
+            return false;
+    }
+    if (p.fuse_softmax) {
+        if (p.N != pick_bn(p.N) || p.out_dtype != DT_BF16 || p.bias || p.temb || p.residual || p.stats_out || p.ups) return false;
+        if (p.softmax_seg < 0 || (p.softmax_seg && (p.N % p.softmax_seg))) return false;
+    }
     if ((p.ld0 % 8) || (p.C1 && (p.ld1 % 8)) || (p.ldb % 8) || (p.ldo % 8) || (p.residual && (p.ldr % 8))) return false;
     if (!wdm_aligned(p.src0, 16) || (p.C1 && !wdm_aligned(p.src1, 16)) || !wdm_aligned(p.B, 16) ||
         !wdm_aligned(p.out, 16) || (p.residual && !wdm_aligned(p.residual, 16)))
@@ -753,12 +842,15 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     a.out_f32 = p.out_dtype == DT_F32;
     a.stats = p.stats_out;
     a.N = p.N;
+    a.softmax = p.fuse_softmax ? 1 : 0;
+    a.softmax_seg = p.softmax_seg;
+    a.nchw_valid = p.out_nchw_valid;
     if (use_pair) return launch_pair<256>(A0, A1, A2, B, a, s);
     const bool allow2 = !a.b_batched || (a.tiles_per_batch % 2 == 0);
-    const int MT = g_force_mt ? (g_force_mt == 2 && allow2 && BN != 64 ? 2 : 1) : pick_mt(a.m_tiles, a.n_tiles, BN, allow2);
-    if (BN == 256) return MT == 2 ? launch_bn<256, 2>(A0, A1, A2, B, a, s) : launch_bn<256, 1>(A0, A1, A2, B, a, s);
+    const int MT = g_force_mt ? (g_force_mt == 2 && allow2 && BN != 256 ? 2 : 1) : pick_mt(a.m_tiles, a.n_tiles, BN, allow2);
+    if (BN == 256) return launch_bn<256, 1>(A0, A1, A2, B, a, s);
     if (BN == 128) return MT == 2 ? launch_bn<128, 2>(A0, A1, A2, B, a, s) : launch_bn<128, 1>(A0, A1, A2, B, a, s);
-    return launch_bn<64, 1>(A0, A1, A2, B, a, s);
+    return MT == 2 ? launch_bn<64, 2>(A0, A1, A2, B, a, s) : launch_bn<64, 1>(A0, A1, A2, B, a, s);
 }
 
 }  // namespace wdm

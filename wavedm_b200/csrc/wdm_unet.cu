@@ -30,6 +30,7 @@ struct ConvSpec {
     void* pw = nullptr;       // packed weights [Cout][taps*Cin_pad] in engine dtype
     float* pb = nullptr;      // bias fp32 [Cout]
     float* pw32 = nullptr;    // fp32 copy (conv_out only)
+    float* pb_pad = nullptr;  // conv_out on the tensor-core path: bias zero-padded to 64
     void* pw_subpix = nullptr;  // upsample convs, bf16 mode: [4 phases][Cout][4 taps][Cin] (sub-pixel decomposition)
 };
 struct GnSpec {
@@ -412,6 +413,21 @@ int pack_model(wdm_unet* net, const float* flat, cudaStream_t s, size_t* total) 
         if (fill && st == WDM_OK)
             st = launch_pack_conv_weight(flat + m.params[c.w].off, c.Cout, c.Cin, 9, c.Cin, c.pw32, DT_F32, 9LL * c.Cin, 0, s);
         copy_f32(c.b, &c.pb);
+        if (dt == DT_BF16 && c.Cout <= 4 && (c.Cin % 64) == 0) {
+            // tensor-core conv_out: Cout zero-padded to one 64-wide N tile
+            c.pw = take((size_t)64 * 9 * c.Cin * es);
+            float* pb64 = reinterpret_cast<float*>(take(64 * 4));
+            if (fill && st == WDM_OK) {
+                cudaError_t e = cudaMemsetAsync(c.pw, 0, (size_t)64 * 9 * c.Cin * es, s);
+                if (e == cudaSuccess) e = cudaMemsetAsync(pb64, 0, 64 * 4, s);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(pb64, flat + m.params[c.b].off, (size_t)c.Cout * 4, cudaMemcpyDeviceToDevice, s);
+                if (e != cudaSuccess) st = wdm_cuda_error((int)e);
+                if (st == WDM_OK)
+                    st = launch_pack_conv_weight(flat + m.params[c.w].off, c.Cout, c.Cin, 9, c.Cin, c.pw, dt, 9LL * c.Cin, 0, s);
+            }
+            c.pb_pad = pb64;
+        }
     }
     *total = off;
     return st;
@@ -630,17 +646,26 @@ Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a, int G) {
     p.out = vT, p.ldo = Lg, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
     run_gemm(c, p);
     free_act(c, n);
-    // S
-    float* S = reinterpret_cast<float*>(c.ar->alloc((size_t)P * L * Lg * 4));
+    // S -> softmax fused in the score GEMM's epilogue (probabilities straight to bf16; the fp32 scores stay in TMEM)
     void* Pm = c.ar->alloc((size_t)P * L * Lg * es);
     if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
     memset(&p, 0, sizeof p);
     p.src0 = qk.p, p.C0 = C, p.ld0 = 2 * C, p.Hin = p.Hout = Hg, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
     p.B = (char*)qk.p + (size_t)C * es, p.b_batch_stride = (long long)Lg * 2 * C, p.ldb = 2 * C, p.b_layout = BL_NK;
     p.M = P * L, p.N = Lg, p.K = C, p.alpha = (float)(1.0 / sqrt((double)C));
-    p.out = S, p.ldo = Lg, p.a_dtype = p.b_dtype = DT_BF16, p.out_dtype = DT_F32;
-    run_gemm(c, p);
-    if (!c.dry() && c.st == WDM_OK) c.fail(launch_softmax_rows(S, P * L, Lg, Pm, DT_BF16, c.s, G > 1 ? L : 0));
+    p.out = Pm, p.ldo = Lg, p.a_dtype = p.b_dtype = DT_BF16, p.out_dtype = DT_BF16;
+    p.fuse_softmax = 1, p.softmax_seg = G > 1 ? L : 0;
+    float* S = nullptr;
+    if (will_use_tc(c, p)) {
+        run_gemm(c, p);
+    } else {
+        p.fuse_softmax = 0, p.softmax_seg = 0, p.out_dtype = DT_F32;
+        S = reinterpret_cast<float*>(c.ar->alloc((size_t)P * L * Lg * 4));
+        if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
+        p.out = S;
+        run_gemm(c, p);
+        if (!c.dry() && c.st == WDM_OK) c.fail(launch_softmax_rows(S, P * L, Lg, Pm, DT_BF16, c.s, G > 1 ? L : 0));
+    }
     free_act(c, qk);
     // O
     Act O = new_act(c, x.H, x.W, C);
@@ -650,7 +675,7 @@ Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a, int G) {
     p.M = P * L, p.N = C, p.K = Lg, p.alpha = 1.f, p.bias = a.qkv.pb + 2 * C;
     p.out = O.p, p.ldo = C, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
     run_gemm(c, p);
-    c.ar->free(S);
+    if (S) c.ar->free(S);
     c.ar->free(Pm);
     c.ar->free(vT);
     Act out = conv_op(c, O, nullptr, a.proj, 1, 0, nullptr, &x, true);
@@ -779,7 +804,22 @@ int forward_impl(wdm_unet* net, Arena* ar, const void* x, const float* t, int T,
     }
     Act n = gn_op(c, h, nullptr, m.norm_out, 1);
     free_act(c, h);
-    if (!c.dry() && c.st == WDM_OK)
+    bool out_done = false;
+    if (m.conv_out.pw && m.conv_out.pb_pad) {
+        GemmParams p;
+        memset(&p, 0, sizeof p);
+        p.src0 = n.p, p.C0 = n.C, p.ld0 = n.C, p.Hin = p.Hout = R, p.Win = p.Wout = R;
+        p.taps = 9, p.stride = 1, p.pad = 1;
+        p.B = m.conv_out.pw, p.ldb = 9 * n.C, p.b_layout = BL_NK;
+        p.M = P * R * R, p.N = 64, p.K = 9 * n.C, p.alpha = 1.f, p.bias = m.conv_out.pb_pad;
+        p.out = eps_out ? (void*)eps_out : reinterpret_cast<void*>(16), p.ldo = 64, p.out_nchw_valid = m.conv_out.Cout;
+        p.a_dtype = p.b_dtype = DT_BF16, p.out_dtype = DT_F32;
+        if (will_use_tc(c, p)) {
+            run_gemm(c, p);
+            out_done = true;
+        }
+    }
+    if (!out_done && !c.dry() && c.st == WDM_OK)
         c.fail(launch_conv_small_cout(n.p, net->dt, P, R, R, n.C, m.conv_out.pw32, m.conv_out.pb, m.conv_out.Cout,
                                       eps_out, s));
     free_act(c, n);
