@@ -131,6 +131,8 @@ WDM_API int wdm_unet_forward(wdm_unet_t* net, const void* x, const float* t, int
 WDM_API int wdm_unet_profile_enable(wdm_unet_t* net, int on);
 WDM_API int wdm_unet_profile_read(wdm_unet_t* net, double* tc_ms, double* tc_flops, long long* tc_launches,
                                   double* simt_ms, double* simt_flops, long long* simt_launches);
+/* algorithmic HBM bytes (each operand / result tensor counted once) of the tensor-core launches since the last call */
+WDM_API double wdm_unet_profile_tc_bytes(wdm_unet_t* net);
 
 /* ------------------------------------------------------------------------------------------------
  * Sampler kernels.

@@ -76,6 +76,7 @@ def load() -> ctypes.CDLL:
         "wdm_launch_counter": (c_longlong, []),
         "wdm_unet_profile_enable": (c_int, [c_void_p, c_int]),
         "wdm_unet_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+        "wdm_unet_profile_tc_bytes": (ctypes.c_double, [c_void_p]),
         "wdm_dwt4x4_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
         "wdm_iwt4x4_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
         "wdm_unet_param_count": (c_int, [c_void_p]),

@@ -274,6 +274,7 @@ struct wdm_unet {
         bool tc;
     };
     std::vector<Span> spans;
+    double tc_bytes = 0;  // algorithmic operand/result bytes of the profiled tensor-core launches
     ~wdm_unet() {
         for (auto& s : spans) {
             cudaEventDestroy(s.a);
@@ -478,6 +479,16 @@ int run_gemm(Ctx& c, const GemmParams& p) {
         cudaEventCreate(&sp.b);
         sp.flops = 2.0 * p.M * p.N * p.K;
         sp.tc = tc;
+        if (tc) {
+            const double es = 2.0, eo = p.out_dtype == DT_F32 ? 4.0 : 2.0;
+            const double rows_in = p.a_shared ? (double)p.Hin * p.Win : (double)p.M / ((double)p.Hout * p.Wout) * p.Hin * p.Win;
+            double b = rows_in * (p.C0 + (p.tail_1x1 ? 0 : p.C1)) * es;                   // main input tensor(s)
+            if (p.tail_1x1) b += (double)p.M * (p.C1 + p.C2) * es;                        // shortcut inputs
+            b += (double)p.N * p.K * es * (p.b_batch_stride ? (double)p.M / ((double)p.Hout * p.Wout) : (p.ups == 2 ? 4.0 : 1.0));
+            b += (double)p.M * (p.out_nchw_valid ? p.out_nchw_valid : p.N) * eo;          // result
+            if (p.residual) b += (double)p.M * p.N * eo;
+            c.net->tc_bytes += b;
+        }
         cudaEventRecord(sp.a, c.s);
     }
     st = tc ? launch_gemm_tc(p, c.s) : launch_gemm_simt(p, c.s);
@@ -960,6 +971,13 @@ extern "C" int wdm_unet_profile_read(wdm_unet_t* net, double* tc_ms, double* tc_
     if (simt_flops) *simt_flops = fl[1];
     if (simt_launches) *simt_launches = n[1];
     return WDM_OK;
+}
+
+extern "C" double wdm_unet_profile_tc_bytes(wdm_unet_t* net) {
+    if (!net) return 0.0;
+    const double b = net->tc_bytes;
+    net->tc_bytes = 0;
+    return b;
 }
 
 extern "C" int wdm_gather_patches(const float* src0, int C0, const float* src1, int C1, const float* src2, int C2,

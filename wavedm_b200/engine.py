@@ -222,4 +222,5 @@ class UNetEngine:
         st = self.lib.wdm_unet_profile_read(self.handle, ctypes.byref(d[0]), ctypes.byref(d[1]), ctypes.byref(n[0]),
                                             ctypes.byref(d[2]), ctypes.byref(d[3]), ctypes.byref(n[1]))
         _lib.check(st, "wdm_unet_profile_read")
+        self.last_tc_bytes = float(self.lib.wdm_unet_profile_tc_bytes(self.handle))
         return d[0].value, d[1].value, n[0].value, d[2].value, d[3].value, n[1].value
