@@ -470,7 +470,7 @@ struct Cfg2 {
     static constexpr int kBBytes = (BN / 2) * kBK * 2;   // this CTA's half of the B tile
     static constexpr int kStage = kABytes + kBBytes;
     static constexpr int kStages = kSmemBudget / kStage;
-    static constexpr int kTmemCols = 2 * BN;
+    static constexpr int kTmemCols = 2 * BN <= 256 ? 256 : 512;  // allocation must be a power of two
     static constexpr int kSmem = kStages * kStage + 1024 + 256;
 };
 
@@ -771,7 +771,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     tile_geom(Hm, Wm, &g);
     const int HWout = Hm * Wm;
     const int npatch = p.a_shared ? 1 : (subpix ? p.M / (4 * HWout) : (p.M + HWout - 1) / HWout);
-    const int BN = pick_bn(p.N);
+    int BN = pick_bn(p.N);
     static const int pair_enabled = []() {
         const char* e = getenv("WDM_TC_PAIR");
         return e ? atoi(e) : 1;
@@ -780,6 +780,14 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     // CTA pairs (cta_group::2) for the 256-wide N tiles: halves the weight-tile traffic out of L2
     const bool use_pair =
         pair_enabled && BN == 256 && ((!p.b_batch_stride && !subpix) || tiles_per_batch_h % 2 == 0);
+    bool pair192 = false;
+    if (use_pair && p.N % 192 == 0 && !p.fuse_softmax) {
+        // 192-wide pair tiles when they fill the 74 CTA pairs better (e.g. N = 768 at 8x8: 64 tiles instead of 48)
+        const long long mt2 = ((p.M + kBM - 1) / kBM + 1) / 2;
+        const long long pairs = num_sms_tc() / 2;
+        auto cost = [&](int bn) { return ((mt2 * (p.N / bn) + pairs - 1) / pairs) * bn; };
+        if (cost(192) < cost(256)) pair192 = true, BN = 192;
+    }
     const int b_box_rows = use_pair ? BN / 2 : BN;
 
     CUtensorMap A0, A1, A2, B;
@@ -845,7 +853,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     a.softmax = p.fuse_softmax ? 1 : 0;
     a.softmax_seg = p.softmax_seg;
     a.nchw_valid = p.out_nchw_valid;
-    if (use_pair) return launch_pair<256>(A0, A1, A2, B, a, s);
+    if (use_pair) return pair192 ? launch_pair<192>(A0, A1, A2, B, a, s) : launch_pair<256>(A0, A1, A2, B, a, s);
     const bool allow2 = !a.b_batched || (a.tiles_per_batch % 2 == 0);
     const int MT = g_force_mt ? (g_force_mt == 2 && allow2 && BN != 256 ? 2 : 1) : pick_mt(a.m_tiles, a.n_tiles, BN, allow2);
     if (BN == 256) return launch_bn<256, 1>(A0, A1, A2, B, a, s);
