@@ -15,12 +15,40 @@ from wavedm_b200.configs import default_config  # noqa: E402
 from wavedm_b200.unet import DiffusionUNet  # noqa: E402
 
 
+def span_table(eng, x, t, out, iters):
+    import collections
+    import tempfile
+    path = os.path.join(tempfile.gettempdir(), f"wdm_spans_{os.getpid()}.csv")
+    os.environ["WDM_PROFILE_DUMP"] = path
+    eng.profile(True)
+    for _ in range(iters):
+        eng.forward_nhwc(x, t, out=out)
+    eng.profile_read()
+    eng.profile(False)
+    del os.environ["WDM_PROFILE_DUMP"]
+    agg = collections.OrderedDict()
+    for line in open(path):
+        tc, M, N, K, taps, W, tag, us, fl = line.strip().split(",")
+        key = (int(tc), int(M), int(N), int(K), int(taps), int(W), int(tag))
+        a = agg.setdefault(key, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += float(us)
+        a[2] += float(fl)
+    os.remove(path)
+    tot = sum(v[1] for v in agg.values()) / iters
+    print(f"contraction launches per forward: {sum(v[0] for v in agg.values()) // iters}, {tot:.1f} us (event-bracketed, no PDL overlap)")
+    print("  tc       M     N      K taps   W tag    n   us/launch  TFLOP/s  share")
+    for k, (n, us, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"  {k[0]:2d} {k[1]:7d} {k[2]:5d} {k[3]:6d} {k[4]:4d} {k[5]:3d} {k[6]:3d} {n // iters:4d} {us / n:10.1f} {fl / us / 1e6:8.1f} {us / iters / tot * 100:5.1f}%")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--patches", type=int, default=64)
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--spans", action="store_true", help="per-shape table of the contraction launches (CUDA events)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     cfg = default_config()
@@ -46,6 +74,8 @@ def main():
         eng.forward_nhwc(x, t, out=out)
         print("profile (tc_ms, tc_flops, tc_n, simt_ms, simt_flops, simt_n):", eng.profile_read())
         eng.profile(False)
+        if a.spans:
+            span_table(eng, x, t, out, a.iters)
     else:
         for _ in range(a.iters):
             eng.forward_nhwc(x, t, out=out)

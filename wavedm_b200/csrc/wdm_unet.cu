@@ -272,6 +272,7 @@ struct wdm_unet {
         cudaEvent_t a, b;
         double flops;
         bool tc;
+        int M, N, K, taps, W, tag;  // shape of the launch (WDM_PROFILE_DUMP)
     };
     std::vector<Span> spans;
     double tc_bytes = 0;  // algorithmic operand/result bytes of the profiled tensor-core launches
@@ -479,6 +480,9 @@ int run_gemm(Ctx& c, const GemmParams& p) {
         cudaEventCreate(&sp.b);
         sp.flops = 2.0 * p.M * p.N * p.K;
         sp.tc = tc;
+        sp.M = p.M, sp.N = p.N, sp.K = p.K, sp.taps = p.taps, sp.W = p.Wout;
+        sp.tag = (p.tail_1x1 ? 1 : 0) | (p.ups == 2 ? 2 : 0) | (p.fuse_softmax ? 4 : 0) | (p.b_batch_stride ? 8 : 0) |
+                 (p.residual ? 16 : 0) | (p.stride == 2 ? 32 : 0);
         if (tc) {
             const double es = 2.0, eo = p.out_dtype == DT_F32 ? 4.0 : 2.0;
             const double rows_in = p.a_shared ? (double)p.Hin * p.Win : (double)p.M / ((double)p.Hout * p.Wout) * p.Hin * p.Win;
@@ -953,6 +957,9 @@ extern "C" int wdm_unet_profile_read(wdm_unet_t* net, double* tc_ms, double* tc_
     if (!net) return WDM_ERR_BAD_ARG;
     double ms[2] = {0, 0}, fl[2] = {0, 0};
     long long n[2] = {0, 0};
+    // WDM_PROFILE_DUMP=<path>: one CSV row per profiled launch (tools/profile_unet.py --spans)
+    FILE* dump = nullptr;
+    if (const char* path = getenv("WDM_PROFILE_DUMP")) dump = fopen(path, "a");
     for (auto& s : net->spans) {
         cudaError_t e = cudaEventSynchronize(s.b);
         if (e != cudaSuccess) return wdm_cuda_error((int)e);
@@ -960,10 +967,12 @@ extern "C" int wdm_unet_profile_read(wdm_unet_t* net, double* tc_ms, double* tc_
         cudaEventElapsedTime(&t, s.a, s.b);
         const int k = s.tc ? 0 : 1;
         ms[k] += t, fl[k] += s.flops, n[k] += 1;
+        if (dump) fprintf(dump, "%d,%d,%d,%d,%d,%d,%d,%.3f,%.6e\n", s.tc ? 1 : 0, s.M, s.N, s.K, s.taps, s.W, s.tag, t * 1e3, s.flops);
         cudaEventDestroy(s.a);
         cudaEventDestroy(s.b);
     }
     net->spans.clear();
+    if (dump) fclose(dump);
     if (tc_ms) *tc_ms = ms[0];
     if (tc_flops) *tc_flops = fl[0];
     if (tc_launches) *tc_launches = n[0];
