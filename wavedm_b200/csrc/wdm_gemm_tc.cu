@@ -189,14 +189,8 @@ __device__ __forceinline__ void epi_stage(const TcArgs& a, int mt0, int nt, int 
         __syncwarp();
     }
     if (a.residual && !a.out_f32) {
-        const uint4* p0 = epi_res_ptr<BN>(a, mt0, nt, row, 0, g);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) r0[q] = p0[q];
-        if (kF > 1) {
-            const uint4* p1 = epi_res_ptr<BN>(a, mt0, nt, row, 1, g);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) r1[q] = p1[q];
-        }
+        ptx::ldg_64B(epi_res_ptr<BN>(a, mt0, nt, row, 0, g), r0);
+        if (kF > 1) ptx::ldg_64B(epi_res_ptr<BN>(a, mt0, nt, row, 1, g), r1);
     }
 }
 
@@ -223,11 +217,7 @@ __device__ __forceinline__ void epi_rows(const TcArgs& a, const CUtensorMap* tmO
         if (res16) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) res_cur[q] = r0[q], r0[q] = r1[q];
-            if (f + 2 < kF) {
-                const uint4* pn = epi_res_ptr<BN>(a, mt0, nt, row, f + 2, g);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) r1[q] = pn[q];
-            }
+            if (f + 2 < kF) ptx::ldg_64B(epi_res_ptr<BN>(a, mt0, nt, row, f + 2, g), r1);
         }
         ptx::tmem_ld_32x32b_x32(tacc + hh * BN + ch * 32, r);
         ptx::tmem_ld_wait();
@@ -973,6 +963,7 @@ bool gemm_tc_supported(const GemmParams& p) {
         !wdm_aligned(p.out, 16) || (p.residual && !wdm_aligned(p.residual, 16)))
         return false;
     if (p.bias && !wdm_aligned(p.bias, 16)) return false;
+    if (p.residual && p.out_dtype == DT_BF16 && (!wdm_aligned(p.residual, 32) || (p.ldr % 16))) return false;  // 256-bit loads
     if (p.temb && (!wdm_aligned(p.temb, 16) || (p.temb_ld % 4))) return false;
     if (p.temb && p.temb_rows > 1 && ((p.Hout * p.Wout) % 32)) return false;  // the epilogue stages one temb row per warp
     if (!p.tail_1x1 && p.K != p.taps * (p.C0 + p.C1)) return false;
