@@ -49,18 +49,48 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--spans", action="store_true", help="per-shape table of the contraction launches (CUDA events)")
+    ap.add_argument("--split", type=int, default=0, help="time the batch as N sub-batches on N streams (tail backfill)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     cfg = default_config()
     torch.manual_seed(61)
     net = DiffusionUNet(cfg)
-    eng = engine.UNetEngine(cfg, net.state_dict(), dev, precision=a.precision, max_patches=a.patches)
+    eng_sd = net.state_dict()
+    eng = engine.UNetEngine(cfg, eng_sd, dev, precision=a.precision, max_patches=a.patches)
     del net
     x = torch.randn(a.patches, 64, 64, eng.cin_pad, device=dev).to(eng.dtype)
     t = torch.tensor([500.0], device=dev)
     out = torch.empty(a.patches, 3, 64, 64, device=dev)
     eng.forward_nhwc(x, t, out=out)
     torch.cuda.synchronize()
+    if a.split > 1:
+        n = a.split
+        Ps = a.patches // n
+        engs = [eng] + [engine.UNetEngine(cfg, eng_sd, dev, precision=a.precision, max_patches=Ps) for _ in range(n - 1)]
+        streams = [torch.cuda.Stream() for _ in range(n)]
+        xs = [x[i * Ps:(i + 1) * Ps].contiguous() for i in range(n)]
+        outs = [torch.empty(Ps, 3, 64, 64, device=dev) for _ in range(n)]
+        torch.cuda.synchronize()
+        def run_split():
+            cur = torch.cuda.current_stream()
+            for i in range(n):
+                streams[i].wait_stream(cur)
+                with torch.cuda.stream(streams[i]):
+                    engs[i].forward_nhwc(xs[i], t, out=outs[i])
+            for i in range(n):
+                cur.wait_stream(streams[i])
+        for _ in range(2):
+            run_split()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(a.iters):
+            run_split()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.iters
+        print(f"P={a.patches} as {n} x {Ps} on {n} streams: {ms:.3f} ms/forward, {79.945e9 * a.patches / ms / 1e9:.1f} TFLOP/s algorithmic")
+        return
     if a.time:
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record()
