@@ -42,7 +42,7 @@ SEED = 61
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU")
@@ -277,6 +277,8 @@ def main():
             dist.gather(out, gathered, dst=0)
         return out
 
+    out_pin = torch.empty(B, 3, H, W).pin_memory()
+
     def step_e2e():
         xh = x_pin.to(dev, non_blocking=True)
         nh = noise_pin.to(dev, non_blocking=True)
@@ -284,7 +286,8 @@ def main():
         out = restorer.restore_batch(xh, r=16, noise=nh, x_other=xo)["output"]
         if world > 1:
             dist.gather(out, gathered, dst=0)
-        return out.to("cpu", non_blocking=False)
+        out_pin.copy_(out, non_blocking=True)  # pinned destination; the timed region ends with a device synchronize
+        return out_pin
 
     def barrier():
         if world > 1:
@@ -365,8 +368,9 @@ def main():
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
                "config": workload_config(args, torch.__version__), "clocks": clk,
-               "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + noise_pin.numel() * 4),
-                       "d2h_bytes_per_step": int(B * 3 * H * W * 4), "ms_per_step": ms_e2e},
+               "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + noise_pin.numel() * 4) * world,
+                       "d2h_bytes_per_step": int(B * 3 * H * W * 4) * world, "ms_per_step": ms_e2e,
+                       "note": "every rank copies its own inputs H2D from pinned memory and its restored images D2H into pinned memory"},
                "gpu_launches": int(launches), "roofline": roof, "roofline_dwt": rdwt, "cpu_baseline": cpu}
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -103,7 +103,10 @@ typedef struct wdm_unet_config {
     int attn_res[8];
     int resolution;     /* data.image_size (patch side R) */
     int in_channels;    /* UNet input channels (models/unet.py:212), 96 for raindrop_wavelet.yml */
-    int out_ch;         /* model.out_ch (<= 4) */
+    int out_ch;         /* model.out_ch (<= 4; 48 with wavelet_in_unet) */
+    int wavelet_in_unet; /* data.wavelet_in_unet (models/unet.py:203-206,349-350,393-394): the network consumes the DWT of
+                            its pixel-domain input (built by wdm_gather_patches_dwt) and wdm_unet_forward applies the IWT
+                            to the 48-channel conv_out result: eps_out is [P, 3, 4R, 4R] */
 } wdm_unet_config;
 
 typedef struct wdm_unet wdm_unet_t;
@@ -121,7 +124,7 @@ WDM_API int wdm_unet_input_channels_padded(const wdm_unet_t* net);
 WDM_API size_t wdm_unet_workspace_bytes(const wdm_unet_t* net, int P);
 /* x: [P, R, R, Cpad] NHWC in the engine's storage type (as produced by wdm_gather_patches);
  * t: device fp32 [T], T == 1 (one timestep for all patches, the sampler's case: ddm_wavelet.py:457) or T == P;
- * eps_out: [P, out_ch, R, R] fp32 NCHW. */
+ * eps_out: [P, out_ch, R, R] fp32 NCHW ([P, 3, 4R, 4R] with wavelet_in_unet). */
 WDM_API int wdm_unet_forward(wdm_unet_t* net, const void* x, const float* t, int T, int P, float* eps_out,
                              void* workspace, size_t workspace_bytes, void* stream);
 /* Per-kernel-class timing of the contraction (conv / GEMM) launches for the roofline report: while enabled,
@@ -147,6 +150,13 @@ WDM_API double wdm_unet_profile_tc_bytes(wdm_unet_t* net);
 WDM_API int wdm_gather_patches(const float* src0, int C0, const float* src1, int C1, const float* src2, int C2, int B,
                                int h, int w, const int* patches, int P, int R, int Cpad, void* out, int out_dtype,
                                void* stream);
+/* wavelet_in_unet mode: crop + DWT + concat + NHWC in one kernel. src0 / src1: fp32 NCHW [B, 3, H, W] pixel-domain images
+ * (already data_transform'ed), patches: (image, hi, wi) in PIXELS, patch side 4R; out: [P, R, R, Cpad], channel
+ * s*48 + 3k + colour (models/unet.py:338-344 all_wavlet_dec on the crops of models/ddm_wavelet.py:467-478). */
+WDM_API int wdm_gather_patches_dwt(const float* src0, const float* src1, int nsrc, int B, int H, int W, const int* patches,
+                                   int P, int R, int Cpad, void* out, int out_dtype, void* stream);
+/* IWT of a row-major fp32 matrix [P*R*R, ld] whose first 48 columns are the sub-bands (3k + colour) -> [P, 3, 4R, 4R] */
+WDM_API int wdm_iwt4x4_nhwc(const float* y, int ld, int P, int R, float* x, void* stream);
 WDM_API int wdm_ddim_step(const float* eps, const int* patches, const int* img_first, int P, int B, int Cp, int R,
                           int h, int w, const float* xt, float* x0_out, float* xt_next, float at, float at_next,
                           void* stream);

@@ -9,6 +9,7 @@ Generates the committed golden vectors under tests/golden/ by importing the UNMO
   * utils/sampling.py:10-13         compute_alpha                            -> ddim_small.npz['alphas']
   * models/ddm_wavelet.py:437-506   generalized_steps_overlapping            -> ddim_small.npz
   * models/ddm_wavelet.py:87-105    get_beta_schedule                        -> ddim_small.npz['betas']
+  * models/unet.py:203-206,338-350  DiffusionUNet(wavelet_in_unet=True) + the pixel-domain sampler -> unet_wiu.npz
   * models/restoration.py:63-168    the DWT -> sample -> x0_preds[-5] -> IWT -> clamp sandwich (config #1,
                                     with HFRM bypassed: x_other = HF bands of the DWT of the synthetic
                                     gt)                                      -> sandwich_full.npz
@@ -55,10 +56,58 @@ def small_cfg():
                             model__attn_resolutions=[8])
 
 
+def wiu_cfg():
+    """data.wavelet_in_unet: True needs out_ch 48, use_other_channels False and in_channels + pred_channels = 96
+    (SURVEY.md A.5); small network, 16x16 sub-band patches = 64x64 pixel patches."""
+    return O.default_config(data__image_size=16, data__patch_size=64, data__wavelet_in_unet=True, model__ch=128,
+                            model__ch_mult=[1, 2], model__num_res_blocks=1, model__attn_resolutions=[8],
+                            model__use_other_channels=False, model__in_channels=93, model__out_ch=48)
+
+
+def golden_wavelet_in_unet(ref_unet, ref_ddm):
+    """models/unet.py:203-206,338-350,393-394 + the pixel-domain sampler (restoration.py:171-172) -> unet_wiu.npz"""
+    cfg = wiu_cfg()
+    torch.manual_seed(61)
+    net = ref_unet.DiffusionUNet(cfg).eval()
+    sd_ref = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd = O.init_state_dict(cfg, seed=61)
+    assert sorted(sd.keys()) == sorted(sd_ref.keys()), "state-dict keys differ (wavelet_in_unet)"
+    assert all(torch.equal(sd[k], sd_ref[k]) for k in sd), "init_state_dict (wavelet_in_unet) is not bit-identical"
+    g = torch.Generator().manual_seed(66)
+    xin = torch.randn(3, 6, 64, 64, generator=g)
+    t = torch.tensor([37.0, 980.0, 500.0])
+    with torch.no_grad():
+        ref_out = net(xin, t)
+        ora_out = O.unet_forward(sd, cfg, xin, t)
+    assert ref_out.shape == (3, 3, 64, 64)
+    assert torch.equal(ref_out, ora_out), float((ref_out - ora_out).abs().max())
+    # the sampler in the pixel domain: one 80x96 image, 64-pixel patches, r = 16 -> 2 x 3 corners, 4 DDIM steps
+    stub = types.SimpleNamespace(config=cfg, num_timesteps=1000, device=torch.device("cpu"))
+    betas = O.beta_schedule(cfg)
+    xc = torch.randn(1, 3, 80, 96, generator=g)
+    x0 = torch.randn(1, 3, 80, 96, generator=g)
+    hl, wl = ref_ddm.DenoisingDiffusion_Wavelet.overlapping_grid_indices(stub, xc, output_size=64, r=16)
+    corners = [(i, j) for i in hl for j in wl]
+    seq = range(0, 1000, 250)
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        xs, x0p = ref_ddm.DenoisingDiffusion_Wavelet.generalized_steps_overlapping(
+            stub, x0, xc, seq, net, betas, eta=0., corners=corners, p_size=64, x_other=None, use_other=False)
+    oxs, ox0p = O.ddim_sample_overlapping(lambda a, tt: O.unet_forward(sd, cfg, a, tt), x0, xc, None, list(seq), betas,
+                                          corners, 64)
+    assert all(torch.equal(a, b) for a, b in zip(xs, oxs)) and all(torch.equal(a, b) for a, b in zip(x0p, ox0p))
+    np.savez(os.path.join(OUT, "unet_wiu.npz"), x=xin.numpy(), t=t.numpy(), out=ref_out.numpy(), seed=61, x_seed=66,
+             x_cond=xc.numpy(), x_noise=x0.numpy(), corners=np.array(corners, np.int32), seq=np.array(list(seq)),
+             xs_last=xs[-1].numpy(), x0_preds=torch.stack(x0p).numpy(), nkeys=len(sd_ref))
+    print("unet_wiu.npz ok; keys", len(sd_ref), "corners", len(corners), "steps", len(x0p))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref_unet, ref_wavelet, ref_ddm, ref_sampling, ref_metrics = import_reference()
+    if "--only-wiu" in sys.argv:   # regenerate just the wavelet_in_unet vectors
+        golden_wavelet_in_unet(ref_unet, ref_ddm)
+        return
 
     # ---------------------------------------------------------------- DWT / IWT
     import pickle
@@ -197,6 +246,7 @@ def main():
     print("patched_full.npz ok; latent range", float(x0p5[-1].min()), float(x0p5[-1].max()))
 
     print("sandwich_full.npz ok; psnr", float(psnr), "latent range", float(lat.min()), float(lat.max()))
+    golden_wavelet_in_unet(ref_unet, ref_ddm)
 
 
 if __name__ == "__main__":

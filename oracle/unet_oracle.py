@@ -128,13 +128,37 @@ def upsample(x: Tensor, sd, p: str) -> Tensor:
     return conv(F.interpolate(x, scale_factor=2.0, mode="nearest"), sd, p + ".conv", padding=1)
 
 
+def haar_conv_weight() -> Tensor:
+    """The `rec4` table of models/wavelet_weights_c2.pkl in closed form: [48, 1, 4, 4], row g*16 + k (SURVEY.md A.1;
+    equality with the pickle is asserted by oracle/make_golden.py)."""
+    return torch.from_numpy(np.tile(haar_packet_matrix(), (3, 1, 1))[:, None].copy())
+
+
+def dwt_torch(x: Tensor) -> Tensor:
+    """models/wavelet.py:37-43 statement for statement (grouped stride-4 conv, then the channel transpose)."""
+    out = F.conv2d(x, haar_conv_weight(), stride=4, groups=3)
+    osz = out.size()
+    return out.view(osz[0], 3, -1, osz[2], osz[3]).transpose(1, 2).contiguous().view(osz)
+
+
+def iwt_torch(y: Tensor) -> Tensor:
+    """models/wavelet.py:44-49 (inverse channel transpose, then the grouped transposed conv)."""
+    sz = y.size()
+    xx = y.view(sz[0], -1, 3, sz[2], sz[3]).transpose(1, 2).contiguous().view(sz)
+    return F.conv_transpose2d(xx, haar_conv_weight(), stride=4, groups=3)
+
+
 def unet_forward(sd: Dict[str, Tensor], cfg, x: Tensor, t: Tensor) -> Tensor:
-    """models/unet.py:346-395 with use_window=False and wavelet_in_unet=False
-    (identical network to models/unet_wav.py:115-155)."""
+    """models/unet.py:346-395 with use_window=False (identical network to models/unet_wav.py:115-155).
+    data.wavelet_in_unet: the DWT of each 3-channel half on the way in (:338-344,349-350), the IWT on the way
+    out (:393-394)."""
     m = cfg.model
     ch, ch_mult, nrb = m.ch, tuple(m.ch_mult), m.num_res_blocks
     nres = len(ch_mult)
     res = cfg.data.image_size
+    wiu = bool(getattr(cfg.data, "wavelet_in_unet", False))
+    if wiu:
+        x = torch.cat([dwt_torch(x[:, :3]), dwt_torch(x[:, 3:])], dim=1)
     assert x.shape[2] == x.shape[3] == res
     temb = timestep_embedding(t, ch)
     temb = F.linear(temb, sd["temb.dense.0.weight"], sd["temb.dense.0.bias"])
@@ -164,7 +188,8 @@ def unet_forward(sd: Dict[str, Tensor], cfg, x: Tensor, t: Tensor) -> Tensor:
             h = upsample(h, sd, f"up.{lv}.upsample")
             cur *= 2
     h = swish(group_norm(h, sd, "norm_out"))
-    return conv(h, sd, "conv_out", padding=1)
+    h = conv(h, sd, "conv_out", padding=1)
+    return iwt_torch(h) if wiu else h
 
 
 def init_state_dict(cfg, seed: int = 61) -> Dict[str, Tensor]:
@@ -201,6 +226,13 @@ def init_state_dict(cfg, seed: int = 61) -> Dict[str, Tensor]:
         for s in ("q", "k", "v", "proj_out"):
             put(name + "." + s, nn.Conv2d(c, c, 1, 1, 0))
 
+    if getattr(cfg.data, "wavelet_in_unet", False):
+        # unet.py:203-206: the two WaveletTransform modules are built first; their default conv init consumes the RNG
+        # before the frozen Haar weights replace it (wavelet.py:19-34)
+        nn.Conv2d(3, 48, 4, 4, 0, groups=3, bias=False)
+        nn.ConvTranspose2d(48, 3, 4, 4, 0, groups=3, bias=False)
+        sd["wavelet_dec.conv.weight"] = haar_conv_weight()
+        sd["wavelet_rec.conv.weight"] = haar_conv_weight()
     put("temb.dense.0", nn.Linear(ch, temb_ch))
     put("temb.dense.1", nn.Linear(temb_ch, temb_ch))
     put("conv_in", nn.Conv2d(cin, ch, 3, 1, 1))

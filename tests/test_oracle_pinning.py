@@ -93,6 +93,38 @@ def test_ddim_oracle_small_vs_reference_golden():
     assert (xs[1] - torch.from_numpy(g["xs_1"])).abs().max() <= 1e-4 * scale
 
 
+def wiu_cfg():
+    return O.default_config(data__image_size=16, data__patch_size=64, data__wavelet_in_unet=True, model__ch=128,
+                            model__ch_mult=[1, 2], model__num_res_blocks=1, model__attn_resolutions=[8],
+                            model__use_other_channels=False, model__in_channels=93, model__out_ch=48)
+
+
+def test_unet_oracle_wavelet_in_unet_vs_reference_golden():
+    """data.wavelet_in_unet (models/unet.py:203-206,338-350,393-394): pixel-domain in / out, DWT and IWT inside forward;
+    and the pixel-domain overlapping-patch DDIM run (restoration.py:171-172)."""
+    g = golden("unet_wiu.npz")
+    cfg = wiu_cfg()
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    assert len(sd) == int(g["nkeys"]) and "wavelet_dec.conv.weight" in sd
+    # the torch restatement of the transform agrees with the C lifting form (summation order only)
+    x6 = torch.from_numpy(g["x"])
+    assert np.abs(O.dwt_torch(x6[:, :3]).numpy() - DO.dwt(g["x"][:, :3].copy())).max() <= 4e-6
+    with torch.no_grad():
+        out = O.unet_forward(sd, cfg, x6, torch.from_numpy(g["t"]))
+    assert out.shape == (3, 3, 64, 64)
+    assert (out - torch.from_numpy(g["out"])).abs().max() <= 2e-5 * max(1.0, float(np.abs(g["out"]).max()))
+    corners = [tuple(int(v) for v in c) for c in g["corners"]]
+    hl, wl = O.overlapping_grid_indices(80, 96, 64, 16)
+    assert corners == [(i, j) for i in hl for j in wl]
+    with torch.no_grad():
+        xs, x0p = O.ddim_sample_overlapping(lambda a, tt: O.unet_forward(sd, cfg, a, tt), torch.from_numpy(g["x_noise"]),
+                                            torch.from_numpy(g["x_cond"]), None, list(g["seq"]), O.beta_schedule(cfg),
+                                            corners, 64)
+    ref = torch.from_numpy(g["x0_preds"])
+    assert (torch.stack(x0p) - ref).abs().max() <= 1e-4 * ref.abs().max()
+    assert (xs[-1] - torch.from_numpy(g["xs_last"])).abs().max() <= 1e-4 * ref.abs().max()
+
+
 def test_grid_indices_cases():
     # SURVEY 8(a) a14: 64^2 -> 1 corner; 128^2 -> 5x5; 120x180 -> 5x9
     assert O.overlapping_grid_indices(64, 64, 64, 16) == ([0], [0])

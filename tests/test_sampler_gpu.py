@@ -223,3 +223,72 @@ def test_restore_with_loader_writes_images_and_matches_restore_batch(tmp_path, c
     res = restorer.restore_batch(x, r=16, want_variants=True)
     assert res["output"].shape == (1, 3, 256, 256) and float(res["output"].min()) >= 0.0 and float(res["output"].max()) <= 1.0
     assert set(res) >= {"output", "cond", "latent", "lrdiff_hrgt", "lrgt_hrwdnet", "lrgt_hrcond", "all_wdnet"}
+
+
+# ---------------------------------------------------------------------------------------------- wavelet_in_unet
+def wiu_cfg():
+    return O.default_config(data__image_size=16, data__patch_size=64, data__wavelet_in_unet=True, model__ch=128,
+                            model__ch_mult=[1, 2], model__num_res_blocks=1, model__attn_resolutions=[8],
+                            model__use_other_channels=False, model__in_channels=93, model__out_ch=48)
+
+
+def test_sampler_wavelet_in_unet_fp32_vs_reference_golden():
+    """The pixel-domain sampler of data.wavelet_in_unet (restoration.py:171-172; DWT / IWT inside the network at every
+    step, unet.py:349-350,393-394) against the trajectory the reference's own classes produced: 2 x 3 overlapping
+    64-pixel patches of one 80x96 image, 4 DDIM steps."""
+    g = golden("unet_wiu.npz")
+    cfg = wiu_cfg()
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    eng = engine.UNetEngine(cfg, sd, DEV, precision="fp32", max_patches=4)  # 6 corners -> chunks of 4 + 2
+    assert eng.patch == 64 and eng.R == 16 and eng.wavelet_in_unet
+    corners = [tuple(c) for c in g["corners"].tolist()]
+    xs, x0p = DdimSampler(eng).sample_lists(torch.from_numpy(g["x_noise"]), torch.from_numpy(g["x_cond"]), None,
+                                            list(g["seq"]), O.beta_schedule(cfg), corners, 64)
+    ref = torch.from_numpy(g["x0_preds"])
+    scale = ref.abs().max().item()
+    assert (torch.stack(x0p) - ref).abs().max().item() <= 1e-4 * scale
+    assert (xs[-1] - torch.from_numpy(g["xs_last"])).abs().max().item() <= 1e-4 * scale
+    # bf16 tensor-core engine on the same run: trajectory stays within the bf16 budget
+    engb = engine.UNetEngine(cfg, sd, DEV, precision="bf16")
+    _, x0b = DdimSampler(engb).sample_lists(torch.from_numpy(g["x_noise"]), torch.from_numpy(g["x_cond"]), None,
+                                            list(g["seq"]), O.beta_schedule(cfg), corners, 64)
+    rel = ((torch.stack(x0b) - ref).pow(2).sum() / ref.pow(2).sum()).sqrt().item()
+    assert rel <= 5e-2, rel
+
+
+def test_restore_batch_wavelet_in_unet_public_api(tmp_path):
+    """DenoisingDiffusion_Wavelet / DiffusiveRestoration with a wavelet_in_unet config: 146-key checkpoint (incl. the
+    frozen wavelet filters) loads strictly, restore_batch returns the clamped x0_preds[-5] in the pixel domain and equals
+    the oracle's run of the same path."""
+    from wavedm_b200.ddm_wavelet import DenoisingDiffusion_Wavelet
+    from wavedm_b200.hfrm import HFRM
+    from wavedm_b200.restoration import DiffusiveRestoration
+    cfg = wiu_cfg()
+    cfg.device = DEV
+    cfg.model.engine_precision = "fp32"
+    sd = O.init_state_dict(cfg, seed=61)
+    torch.manual_seed(5)
+    hpath = os.path.join(tmp_path, "hfrm.pth")
+    torch.save(HFRM(in_channel=3, dim=32, mid_blk_num=6, enc_blk_nums=[2, 2, 2, 4], dec_blk_nums=[2, 2, 2, 2]).state_dict(), hpath)
+    ck = os.path.join(tmp_path, "ddpm.pth.tar")
+    opt = torch.optim.Adam([torch.nn.Parameter(v.clone()) for v in sd.values()], lr=4e-5, eps=1e-8)
+    torch.save({"epoch": 1, "step": 2, "state_dict": sd, "optimizer": opt.state_dict(),
+                "ema_helper": {k: v.clone() for k, v in sd.items()}, "params": None, "config": None}, ck)
+    args = argparse.Namespace(resume=ck, local_rank=0, sampling_timesteps=6, grid_r=16, image_folder=str(tmp_path),
+                              hfrm_ckpt=hpath, test_set="raindrop")
+    diffusion = DenoisingDiffusion_Wavelet(args, cfg)
+    restorer = DiffusiveRestoration(diffusion, args, cfg)
+    gen = torch.Generator().manual_seed(12)
+    ximg = torch.rand(2, 6, 64, 80, generator=gen)
+    noise = torch.randn(2, 3, 64, 80, generator=gen)
+    res = restorer.restore_batch(ximg, r=16, noise=noise.to(DEV))
+    out = res["output"].cpu()
+    assert out.shape == (2, 3, 64, 80) and float(out.min()) >= 0.0 and float(out.max()) <= 1.0
+    x_cond = 2 * ximg[:, :3] - 1.0
+    hl, wl = O.overlapping_grid_indices(64, 80, 64, 16)
+    corners = [(i, j) for i in hl for j in wl]
+    with torch.no_grad():
+        _, x0p = O.ddim_sample_overlapping(lambda a, tt: O.unet_forward(sd, cfg, a, tt), noise, x_cond, None,
+                                           O.sampling_seq(1000, 6), O.beta_schedule(cfg), corners, 64)
+    ref = torch.clamp((x0p[-5] + 1.0) / 2.0, 0.0, 1.0)
+    assert (out - ref).abs().max().item() < 1e-3

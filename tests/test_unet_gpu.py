@@ -1,6 +1,7 @@
 """GPU parity of the UNet engine and its kernels against the torch-fp32 oracle (oracle/unet_oracle.py, itself
 pinned to the reference module by tests/golden/*) -- through the C ABI."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -13,6 +14,7 @@ from wavedm_b200 import _lib, engine
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda", 0)
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def small_cfg():
@@ -429,3 +431,119 @@ def test_workspace_too_small_is_reported():
     assert st == _lib.WDM_ERR_WORKSPACE
     with pytest.raises(KeyError):
         engine.UNetEngine(cfg, {k: v for k, v in sd.items() if k != "conv_in.bias"}, DEV, precision="fp32")
+
+
+_VARIANT_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {tests!r}); sys.path.insert(0, {repo!r})
+from test_unet_gpu import run_conv, ref_conv
+from wavedm_b200 import _lib
+g = torch.Generator().manual_seed(5)
+rb = lambda t: t.bfloat16().float()
+P, C, H = {P}, 128, 64
+x = rb(torch.randn(P, C, H, H, generator=g)); w = rb(torch.randn(128, C, 3, 3, generator=g) / (3 * C ** 0.5))
+bias = torch.randn(128, generator=g); temb = torch.randn(1, 128, generator=g); res = rb(torch.randn(P, 128, H, H, generator=g))
+ref = ref_conv(x, None, w, bias, 1, 0, temb, res)
+out, stats = run_conv(x, None, w, bias, 1, 0, temb, res, 1, _lib.WDM_GEMM_IMPL_TC, want_stats=True)
+scale = max(1.0, ref.abs().max().item())
+assert (out - ref).abs().max().item() <= 6e-3 * scale
+rows = ref.permute(0, 2, 3, 1).reshape(-1, 128); blk = rows.reshape(rows.shape[0] // 32, 32, 32, 4)
+s_ref = torch.stack([blk.sum(dim=(1, 3)), (blk ** 2).sum(dim=(1, 3))], dim=-1)
+assert not torch.isnan(stats).any() and (stats - s_ref).abs().max().item() <= 2e-3 * max(1.0, s_ref.abs().max().item())
+print("variant ok")
+"""
+
+
+@pytest.mark.parametrize("env,P", [({"WDM_TC_SWAP": "1"}, 3), ({"WDM_TC_PAIR128X2": "1"}, 19), ({"WDM_TC_EPI_TMA": "0"}, 3)])
+def test_gemm_tc_level0_variants(env, P):
+    """The env-gated level-0 kernel variants (swap-AB accumulator, CTA pairs with two m-tiles per CTA, direct-store
+    epilogue) stay bit-for-tolerance equal to the default path: Cout = 128 conv @64x64 with bias, temb, residual and the
+    GroupNorm side-car. The switches are read once per process, hence the subprocess. P = 19: 304 m-tiles (>= 4 per CTA
+    pair, an odd count of 4-tile super-tiles)."""
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env)
+    src = _VARIANT_SCRIPT.format(tests=os.path.dirname(os.path.abspath(__file__)), repo=REPO, P=P)
+    r = subprocess.run([sys.executable, "-c", src], env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout + r.stderr
+
+
+# ---------------------------------------------------------------------------------------------- wavelet_in_unet
+def wiu_cfg():
+    return O.default_config(data__image_size=16, data__patch_size=64, data__wavelet_in_unet=True, model__ch=128,
+                            model__ch_mult=[1, 2], model__num_res_blocks=1, model__attn_resolutions=[8],
+                            model__use_other_channels=False, model__in_channels=93, model__out_ch=48)
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_gather_patches_dwt_vs_oracle(dtype):
+    """Fused crop + DWT + concat + NHWC (wdm_gather_patches_dwt) == the C oracle's lifting-form DWT of the crops, bit for
+    bit in fp32 (bf16: the same values rounded once); unaligned pixel corners; pad channels are zero."""
+    from oracle import dwt_oracle as DO
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    B, H, W, R, Cpad = 2, 44, 52, 8, 128 if dtype else 96
+    a, b = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 3, H, W, generator=g)
+    pats = torch.tensor([[0, 0, 0], [1, 12, 20], [0, 5, 3], [1, 7, 17]], dtype=torch.int32)
+    td = torch.bfloat16 if dtype else torch.float32
+    out = torch.full((len(pats), R, R, Cpad), 7.0, dtype=td, device=DEV)
+    ad, bd, pd = a.to(DEV), b.to(DEV), pats.to(DEV)
+    st = lib.wdm_gather_patches_dwt(ad.data_ptr(), bd.data_ptr(), 2, B, H, W, pd.data_ptr(), len(pats), R, Cpad,
+                                    out.data_ptr(), dtype, torch.cuda.current_stream().cuda_stream)
+    _lib.check(st, "wdm_gather_patches_dwt")
+    torch.cuda.synchronize()
+    for q, (n, hi, wi) in enumerate(pats.tolist()):
+        crops = [t[n:n + 1, :, hi:hi + 4 * R, wi:wi + 4 * R].contiguous().numpy() for t in (a, b)]
+        ref = np.concatenate([DO.dwt(c) for c in crops], axis=1)[0]            # [96, R, R]
+        got = out[q].float().cpu().numpy().transpose(2, 0, 1)                     # [Cpad, R, R]
+        if dtype == 0:
+            assert np.array_equal(got[:96], ref)
+        else:
+            assert np.array_equal(got[:96], torch.from_numpy(ref).bfloat16().float().numpy())
+        assert not got[96:].any()
+    # error behaviour: patch larger than the image
+    assert lib.wdm_gather_patches_dwt(ad.data_ptr(), bd.data_ptr(), 2, B, H, W, pd.data_ptr(), 1, 16, Cpad,
+                                      out.data_ptr(), dtype, 0) == _lib.WDM_ERR_BAD_SHAPE
+
+
+@pytest.mark.parametrize("ld", [48, 64])
+def test_iwt_nhwc_vs_oracle(ld):
+    from oracle import dwt_oracle as DO
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(4)
+    P, R = 3, 8
+    y = torch.randn(P, R, R, ld, generator=g)
+    x = torch.empty(P, 3, 4 * R, 4 * R, device=DEV)
+    yd = y.to(DEV)
+    _lib.check(lib.wdm_iwt4x4_nhwc(yd.data_ptr(), ld, P, R, x.data_ptr(), torch.cuda.current_stream().cuda_stream),
+               "wdm_iwt4x4_nhwc")
+    torch.cuda.synchronize()
+    ref = DO.iwt(y[..., :48].permute(0, 3, 1, 2).contiguous().numpy())
+    assert np.array_equal(x.cpu().numpy(), ref)
+
+
+def test_unet_wavelet_in_unet_vs_reference_golden():
+    """DiffusionUNet(wavelet_in_unet=True): pixel-domain [P,6,64,64] -> [P,3,64,64] against the reference module's own
+    output (golden): fp32 engine <= 5e-5 relative, bf16 tensor-core engine <= 3e-2 relative L2."""
+    g = golden("unet_wiu.npz")
+    cfg = wiu_cfg()
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    x, t = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["t"]).to(DEV)
+    ref = torch.from_numpy(g["out"])
+    scale = ref.abs().max().item()
+    e32 = engine.UNetEngine(cfg, sd, DEV, precision="fp32")
+    out = e32.forward(x, t).cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() <= 5e-5 * max(1.0, scale)
+    e16 = engine.UNetEngine(cfg, sd, DEV, precision="bf16")
+    n0 = _lib.load().wdm_launch_counter()
+    outb = e16.forward(x, t).cpu()
+    assert _lib.load().wdm_launch_counter() > n0
+    rel = ((outb - ref).pow(2).sum() / ref.pow(2).sum()).sqrt().item()
+    assert rel <= 3e-2, rel
+    # the broadcast-t form the sampler uses
+    out1 = e32.forward(x, t[:1]).cpu()
+    with torch.no_grad():
+        ref1 = O.unet_forward(sd, cfg, torch.from_numpy(g["x"]), torch.from_numpy(g["t"][:1]))
+    assert (out1 - ref1).abs().max().item() <= 5e-5 * max(1.0, ref1.abs().max().item())

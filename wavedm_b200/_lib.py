@@ -91,6 +91,9 @@ def load() -> ctypes.CDLL:
                                      c_void_p]),
         "wdm_gather_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                        c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+        "wdm_gather_patches_dwt": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                           c_void_p, c_int, c_void_p]),
+        "wdm_iwt4x4_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
         "wdm_ddim_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_float, c_float, c_void_p]),
         "wdm_gemm": (c_int, [c_void_p, c_int, c_void_p]),

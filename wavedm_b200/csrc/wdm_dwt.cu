@@ -150,6 +150,74 @@ __global__ void __launch_bounds__(256) iwt4x4_direct_kernel(const float* __restr
     }
 }
 
+// ---- wavelet_in_unet variants (models/unet.py:338-350, 393-394) -----------------------------------------------
+// DiffusionUNet(wavelet_in_unet=True) applies the DWT to each 3-channel half of its pixel-domain input INSIDE forward()
+// and the IWT to its 48-channel output, i.e. once per DDIM step. Here the forward transform is fused with the sampler's
+// crop + concat + NHWC conversion (ddm_wavelet.py:467-478) and the inverse reads the conv_out result in place:
+//   dwt_gather : fp32 NCHW image-level sources [B,3,H,W] x nsrc, cropped at (hi, wi) in PIXELS, side 4R
+//                -> UNet input [P, R, R, Cpad] NHWC (channel s*48 + 3k + g, engine dtype), pad channels zero.
+//   iwt_nhwc   : conv_out result [P*R*R, ld] fp32 (first 48 columns) -> eps [P, 3, 4R, 4R] fp32 NCHW.
+// One CTA per (sub-band row i, patch): thread (plane = s*3+g, j) owns one 4x4 pixel block; the row of R pixels x Cpad
+// channels is staged in shared memory so that the global store is one contiguous run.
+template <typename TO>
+__global__ void __launch_bounds__(384) dwt_gather_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
+                                                        int nsrc, int H, int W, const int* __restrict__ patches, int R,
+                                                        int Cpad, TO* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_dg[];
+    TO* tile = reinterpret_cast<TO*>(smem_dg);  // [R][Cpad]
+    const int i = blockIdx.x, pi = blockIdx.y;
+    const int img = patches[pi * 3], hi = patches[pi * 3 + 1], wi = patches[pi * 3 + 2];
+    const int nplanes = nsrc * 3;
+    for (int e = threadIdx.x; e < R * Cpad; e += blockDim.x) {
+        const int c = e % Cpad;
+        if (c >= nplanes * 16) tile[e] = TO(0.f);
+    }
+    for (int u = threadIdx.x; u < nplanes * R; u += blockDim.x) {
+        const int plane = u / R, j = u - plane * R;
+        const int sidx = plane / 3, g = plane - 3 * sidx;
+        const float* src = (sidx == 0 ? src0 : src1) + (((long long)img * 3 + g) * H + (hi + 4 * i)) * W + (wi + 4 * j);
+        float v[4][4];
+        const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((W & 3) == 0);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (vec) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(src + (long long)r * W));
+                v[r][0] = q.x, v[r][1] = q.y, v[r][2] = q.z, v[r][3] = q.w;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[r][c] = __ldg(src + (long long)r * W + c);
+            }
+        }
+        float o[16];
+        wht16_fwd(v, o);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) tile[j * Cpad + sidx * 48 + 3 * k + g] = TO(o[k]);
+    }
+    __syncthreads();
+    TO* dst = out + ((long long)pi * R + i) * R * Cpad;
+    const int n16 = R * Cpad * (int)sizeof(TO) / 16;
+    for (int e = threadIdx.x; e < n16; e += blockDim.x)
+        reinterpret_cast<uint4*>(dst)[e] = reinterpret_cast<const uint4*>(tile)[e];
+}
+
+__global__ void __launch_bounds__(192) iwt_nhwc_kernel(const float* __restrict__ y, int ld, int R, float* __restrict__ x) {
+    const int i = blockIdx.x, pi = blockIdx.y;
+    for (int u = threadIdx.x; u < 3 * R; u += blockDim.x) {
+        const int g = u / R, j = u - g * R;
+        const float* src = y + (((long long)pi * R + i) * R + j) * ld + g;
+        float in[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) in[k] = __ldg(src + 3 * k);
+        float v[4][4];
+        wht16_inv(in, v);
+        const int Wp = 4 * R;
+        float* dst = x + (((long long)pi * 3 + g) * Wp + 4 * i) * Wp + 4 * j;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            *reinterpret_cast<float4*>(dst + (long long)r * Wp) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+    }
+}
+
 // ---- TMA variants -------------------------------------------------------------------------------------
 constexpr int kTW = 128;         // pixel tile width
 constexpr int kTH = 32;          // pixel tile height
@@ -431,4 +499,47 @@ extern "C" int wdm_iwt4x4_fwd(const float* y, float* x, int n, int h, int w, int
     else
         iwt4x4_direct_kernel<false><<<(unsigned)grid, 256, 0, stream>>>(y, x, nblocks, h, w);
     return wdm_launch_status();
+}
+
+
+// ---- wavelet_in_unet entry points ---------------------------------------------------------------------
+namespace wdm {
+int launch_dwt_gather(const float* src0, const float* src1, int nsrc, int B, int H, int W, const int* patches, int P, int R,
+                      int Cpad, void* out, int out_dtype, cudaStream_t s) {
+    if (P <= 0) return WDM_OK;
+    if (!src0 || nsrc < 1 || nsrc > 2 || (nsrc == 2 && !src1) || !patches || !out) return WDM_ERR_BAD_ARG;
+    if (R <= 0 || 4 * R > H || 4 * R > W || Cpad < nsrc * 48 || (Cpad % 8) || B <= 0) return WDM_ERR_BAD_SHAPE;
+    if (!wdm_aligned(out, 16)) return WDM_ERR_BAD_ALIGN;
+    const size_t es = out_dtype == 0 ? 4 : 2;
+    const size_t smem = (size_t)R * Cpad * es;
+    if (smem > 96 * 1024) return WDM_ERR_BAD_SHAPE;
+    dim3 grid(R, P);
+    if (out_dtype == 0) {
+        cudaFuncSetAttribute(dwt_gather_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        dwt_gather_kernel<float><<<grid, 384, smem, s>>>(src0, src1, nsrc, H, W, patches, R, Cpad, reinterpret_cast<float*>(out));
+    } else {
+        cudaFuncSetAttribute(dwt_gather_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        dwt_gather_kernel<__nv_bfloat16><<<grid, 384, smem, s>>>(src0, src1, nsrc, H, W, patches, R, Cpad,
+                                                                  reinterpret_cast<__nv_bfloat16*>(out));
+    }
+    return wdm_launch_status();
+}
+
+int launch_iwt_nhwc(const float* y, int ld, int P, int R, float* x, cudaStream_t s) {
+    if (P <= 0) return WDM_OK;
+    if (!y || !x || ld < 48 || R <= 0) return WDM_ERR_BAD_ARG;
+    if (!wdm_aligned(x, 16)) return WDM_ERR_BAD_ALIGN;
+    iwt_nhwc_kernel<<<dim3(R, P), 192, 0, s>>>(y, ld, R, x);
+    return wdm_launch_status();
+}
+}  // namespace wdm
+
+extern "C" int wdm_gather_patches_dwt(const float* src0, const float* src1, int nsrc, int B, int H, int W, const int* patches,
+                                      int P, int R, int Cpad, void* out, int out_dtype, void* stream) {
+    if (out_dtype != WDM_PREC_FP32 && out_dtype != WDM_PREC_BF16) return WDM_ERR_BAD_ARG;
+    return wdm::launch_dwt_gather(src0, src1, nsrc, B, H, W, patches, P, R, Cpad, out, out_dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int wdm_iwt4x4_nhwc(const float* y, int ld, int P, int R, float* x, void* stream) {
+    return wdm::launch_iwt_nhwc(y, ld, P, R, x, static_cast<cudaStream_t>(stream));
 }

@@ -80,6 +80,10 @@ struct GatherParams {
     int out_dtype;
 };
 int launch_gather_patches(const GatherParams& p, cudaStream_t stream);
+// wavelet_in_unet (wdm_dwt.cu): fused crop + DWT + concat + NHWC gather, and the IWT of the NHWC conv_out result
+int launch_dwt_gather(const float* src0, const float* src1, int nsrc, int B, int H, int W, const int* patches, int P, int R,
+                      int Cpad, void* out, int out_dtype, cudaStream_t stream);
+int launch_iwt_nhwc(const float* y, int ld, int P, int R, float* x, cudaStream_t stream);
 
 // Fused overlap-average + DDIM update (models/ddm_wavelet.py:485-503, eta = 0), per image pixel:
 //   et = sum_{patches covering the pixel} eps_patch / count ; x0 = (xt - et*sqrt(1-at))/sqrt(at)

@@ -127,8 +127,10 @@ bool attn_at(const wdm_unet_config& c, int res) {
 // models/unet.py:196-307 -- same construction order, so the parameter list is the reference's module order.
 int build_model(const wdm_unet_config& cfg, Model* m) {
     if (cfg.ch <= 0 || cfg.ch % 128 || cfg.n_levels < 1 || cfg.n_levels > 8 || cfg.num_res_blocks < 1 ||
-        cfg.n_attn_res < 0 || cfg.n_attn_res > 8 || cfg.in_channels < 1 || cfg.out_ch < 1 || cfg.out_ch > 4)
+        cfg.n_attn_res < 0 || cfg.n_attn_res > 8 || cfg.in_channels < 1 || cfg.out_ch < 1)
         return WDM_ERR_BAD_ARG;
+    // wavelet_in_unet: the DWT of the two 3-channel halves feeds the network, the IWT consumes 48 output channels
+    if (cfg.wavelet_in_unet ? (cfg.out_ch != 48 || cfg.in_channels != 96) : cfg.out_ch > 4) return WDM_ERR_BAD_ARG;
     if (cfg.resolution < (1 << (cfg.n_levels - 1)) * 2 || (cfg.resolution % (1 << (cfg.n_levels - 1))))
         return WDM_ERR_BAD_SHAPE;
     for (int i = 0; i < cfg.n_levels; ++i)
@@ -415,7 +417,7 @@ int pack_model(wdm_unet* net, const float* flat, cudaStream_t s, size_t* total) 
         if (fill && st == WDM_OK)
             st = launch_pack_conv_weight(flat + m.params[c.w].off, c.Cout, c.Cin, 9, c.Cin, c.pw32, DT_F32, 9LL * c.Cin, 0, s);
         copy_f32(c.b, &c.pb);
-        if (dt == DT_BF16 && c.Cout <= 4 && (c.Cin % 64) == 0) {
+        if (dt == DT_BF16 && c.Cout <= 64 && (c.Cin % 64) == 0) {
             // tensor-core conv_out: Cout zero-padded to one 64-wide N tile
             c.pw = take((size_t)64 * 9 * c.Cin * es);
             float* pb64 = reinterpret_cast<float*>(take(64 * 4));
@@ -820,7 +822,30 @@ int forward_impl(wdm_unet* net, Arena* ar, const void* x, const float* t, int T,
     Act n = gn_op(c, h, nullptr, m.norm_out, 1);
     free_act(c, h);
     bool out_done = false;
-    if (m.conv_out.pw && m.conv_out.pb_pad) {
+    if (m.cfg.wavelet_in_unet) {
+        // conv_out -> [P*R*R][ld] fp32 (NHWC rows, 48 valid columns) -> IWT -> eps_out [P, 3, 4R, 4R]  (unet.py:393-394)
+        const bool tc_out = net->dt == DT_BF16 && m.conv_out.pw && m.conv_out.pb_pad;  // bf16: Cout zero-padded to 64
+        const int ld = tc_out ? 64 : m.conv_out.Cout;
+        float* tmp = reinterpret_cast<float*>(ar->alloc((size_t)P * R * R * ld * sizeof(float)));
+        if (ar->failed) c.fail(WDM_ERR_WORKSPACE);
+        GemmParams p;
+        memset(&p, 0, sizeof p);
+        p.src0 = n.p, p.C0 = n.C, p.ld0 = n.C, p.Hin = p.Hout = R, p.Win = p.Wout = R;
+        p.taps = 9, p.stride = 1, p.pad = 1;
+        p.b_layout = BL_NK, p.ldb = 9 * n.C;
+        p.M = P * R * R, p.K = 9 * n.C, p.alpha = 1.f;
+        p.out = tmp ? (void*)tmp : reinterpret_cast<void*>(16), p.ldo = ld, p.out_dtype = DT_F32;
+        if (tc_out) {
+            p.B = m.conv_out.pw, p.N = 64, p.bias = m.conv_out.pb_pad, p.a_dtype = p.b_dtype = DT_BF16;
+        } else {
+            p.B = m.conv_out.pw32, p.N = m.conv_out.Cout, p.bias = m.conv_out.pb, p.a_dtype = net->dt, p.b_dtype = DT_F32;
+        }
+        run_gemm(c, p);
+        if (!c.dry() && c.st == WDM_OK) c.fail(launch_iwt_nhwc(tmp, ld, P, R, eps_out, s));
+        ar->free(tmp);
+        out_done = true;
+    }
+    if (!out_done && m.conv_out.pw && m.conv_out.pb_pad) {
         GemmParams p;
         memset(&p, 0, sizeof p);
         p.src0 = n.p, p.C0 = n.C, p.ld0 = n.C, p.Hin = p.Hout = R, p.Win = p.Wout = R;

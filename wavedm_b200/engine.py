@@ -20,7 +20,8 @@ PREC = {"fp32": _lib.WDM_PREC_FP32, "bf16": _lib.WDM_PREC_BF16}
 class WdmUnetConfig(ctypes.Structure):
     _fields_ = [("ch", ctypes.c_int), ("n_levels", ctypes.c_int), ("ch_mult", ctypes.c_int * 8),
                 ("num_res_blocks", ctypes.c_int), ("n_attn_res", ctypes.c_int), ("attn_res", ctypes.c_int * 8),
-                ("resolution", ctypes.c_int), ("in_channels", ctypes.c_int), ("out_ch", ctypes.c_int)]
+                ("resolution", ctypes.c_int), ("in_channels", ctypes.c_int), ("out_ch", ctypes.c_int),
+                ("wavelet_in_unet", ctypes.c_int)]
 
 
 def unet_in_channels(config) -> int:
@@ -48,6 +49,7 @@ def make_config_struct(config) -> WdmUnetConfig:
     c.resolution = int(config.data.image_size)
     c.in_channels = unet_in_channels(config)
     c.out_ch = int(m.out_ch)
+    c.wavelet_in_unet = 1 if getattr(config.data, "wavelet_in_unet", False) else 0
     return c
 
 
@@ -75,8 +77,8 @@ def temb_freqs(ch: int) -> torch.Tensor:
 class UNetEngine:
     def __init__(self, config, state_dict: Dict[str, torch.Tensor], device, precision: str = "bf16", flags: int = 0,
                  max_patches: int = 64):
-        if getattr(config.data, "use_window", False) or getattr(config.data, "wavelet_in_unet", False):
-            raise NotImplementedError("use_window / wavelet_in_unet variants are not implemented (SURVEY 8f-4)")
+        if getattr(config.data, "use_window", False):
+            raise NotImplementedError("the use_window variant is not implemented (SURVEY 8f-4)")
         if getattr(config.data, "global_attn", False):
             raise NotImplementedError("global_attn (DiffusionUNet_Global) is out of scope")
         if float(getattr(config.model, "dropout", 0.0)) != 0.0:
@@ -90,11 +92,16 @@ class UNetEngine:
         self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
         self.cstruct = make_config_struct(config)
         self.R = int(config.data.image_size)
-        self.out_ch = int(config.model.out_ch)
-        self.in_channels = self.cstruct.in_channels
+        # wavelet_in_unet (models/unet.py:203-206): the module consumes pixel-domain [P, 6, 4R, 4R] and returns [P, 3, 4R, 4R]
+        self.wavelet_in_unet = bool(self.cstruct.wavelet_in_unet)
+        self.patch = 4 * self.R if self.wavelet_in_unet else self.R      # side of a sampler patch / of eps
+        self.out_ch = 3 if self.wavelet_in_unet else int(config.model.out_ch)
+        self.in_channels = 6 if self.wavelet_in_unet else self.cstruct.in_channels  # channels the CALLER concatenates
         self.max_patches = int(max_patches)
         table = param_table(self.cstruct)
         sd = {k[7:] if k.startswith("module.") else k: v for k, v in state_dict.items()}
+        # the frozen wavelet filters of a wavelet_in_unet module (unet.py:205-206) are not engine parameters
+        sd = {k: v for k, v in sd.items() if not k.startswith(("wavelet_dec.", "wavelet_rec."))}
         chunks = []
         for name, numel in table:
             if name == "temb.freqs":
@@ -157,6 +164,17 @@ class UNetEngine:
         B, _, h, w = srcs[0].shape
         if out is None:
             out = torch.empty((P, self.R, self.R, self.cin_pad), dtype=self.dtype, device=self.device)
+        if self.wavelet_in_unet:
+            # crop (pixel coordinates, side 4R) + DWT of every 3-channel source + concat + NHWC in one kernel
+            assert 1 <= len(srcs) <= 2
+            for s_ in srcs:
+                assert s_.is_cuda and s_.dtype == torch.float32 and s_.is_contiguous() and s_.shape == (B, 3, h, w)
+            with torch.cuda.device(self.device):
+                st = self.lib.wdm_gather_patches_dwt(srcs[0].data_ptr(), srcs[1].data_ptr() if len(srcs) > 1 else 0,
+                                                     len(srcs), B, h, w, patches.data_ptr(), P, self.R, self.cin_pad,
+                                                     out.data_ptr(), self.prec, _lib.current_stream_ptr(self.device))
+            _lib.check(st, "wdm_gather_patches_dwt")
+            return out
         ptr = [0, 0, 0]
         cs = [0, 0, 0]
         for i, s in enumerate(srcs):
@@ -170,12 +188,13 @@ class UNetEngine:
         return out
 
     def forward_nhwc(self, x: torch.Tensor, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x: [P, R, R, cin_pad] engine dtype; t: fp32 device [1] or [P]. Returns eps [P, out_ch, R, R] fp32."""
+        """x: [P, R, R, cin_pad] engine dtype; t: fp32 device [1] or [P]. Returns eps [P, out_ch, patch, patch] fp32
+        (patch = R, or 4R in wavelet_in_unet mode where the IWT is applied to the 48-channel conv_out result)."""
         P = x.shape[0]
         assert x.dtype == self.dtype and x.is_contiguous() and x.shape[1:] == (self.R, self.R, self.cin_pad)
         assert t.dtype == torch.float32 and t.is_cuda and t.numel() in (1, P)
         if out is None:
-            out = torch.empty((P, self.out_ch, self.R, self.R), dtype=torch.float32, device=self.device)
+            out = torch.empty((P, self.out_ch, self.patch, self.patch), dtype=torch.float32, device=self.device)
         ws = self.workspace(P)
         wptr = self._aligned_ptr(ws)
         with torch.cuda.device(self.device):
@@ -187,7 +206,7 @@ class UNetEngine:
     def forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         """Module-level entry: x [P, Cin, R, R] fp32 NCHW, t [1] or [P] (models/unet.py:346)."""
         P = x.shape[0]
-        assert x.shape[1] == self.in_channels and x.shape[2] == x.shape[3] == self.R
+        assert x.shape[1] == self.in_channels and x.shape[2] == x.shape[3] == self.patch
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
         t = t.to(device=self.device, dtype=torch.float32).contiguous()
         outs = []
@@ -196,7 +215,7 @@ class UNetEngine:
             n = xc.shape[0]
             patches = torch.zeros((n, 3), dtype=torch.int32, device=self.device)
             patches[:, 0] = torch.arange(n, dtype=torch.int32, device=self.device)
-            xin = self.gather([xc], patches)
+            xin = self.gather([xc[:, :3].contiguous(), xc[:, 3:].contiguous()] if self.wavelet_in_unet else [xc], patches)
             tc = t if t.numel() == 1 else t[i:i + n].contiguous()
             outs.append(self.forward_nhwc(xin, tc))
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
@@ -206,7 +225,7 @@ class UNetEngine:
         P = eps.shape[0]
         B, Cp, h, w = xt.shape
         with torch.cuda.device(self.device):
-            st = self.lib.wdm_ddim_step(eps.data_ptr(), patches.data_ptr(), img_first.data_ptr(), P, B, Cp, self.R, h, w,
+            st = self.lib.wdm_ddim_step(eps.data_ptr(), patches.data_ptr(), img_first.data_ptr(), P, B, Cp, self.patch, h, w,
                                         xt.data_ptr(), x0_out.data_ptr(), xt_next.data_ptr(), ctypes.c_float(at),
                                         ctypes.c_float(at_next), _lib.current_stream_ptr(self.device))
         _lib.check(st, "wdm_ddim_step")

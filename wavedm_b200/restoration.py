@@ -38,10 +38,13 @@ class DiffusiveRestoration:
         else:
             print('Pre-trained diffusion model path is missing!')
         d = config.data
-        if getattr(d, "lap", False) or getattr(d, "global_attn", False) or getattr(d, "wavelet_in_unet", False) \
-                or not getattr(d, "wavelet", True) or d.dataset == "DPD_Dual":
-            raise NotImplementedError("only the raindrop_wavelet.yml mode (wavelet=True, wavelet_in_unet=False, "
-                                      "lap=False, global_attn=False) is implemented (SURVEY.md 2.1 / 8f-4)")
+        if getattr(d, "lap", False) or getattr(d, "global_attn", False) or not getattr(d, "wavelet", True) \
+                or d.dataset == "DPD_Dual":
+            raise NotImplementedError("only wavelet=True configs (raindrop_wavelet.yml, optionally wavelet_in_unet) with "
+                                      "lap=False, global_attn=False are implemented (SURVEY.md 2.1 / 8f-4)")
+        if getattr(d, "wavelet_in_unet", False) and config.model.use_other_channels:
+            raise NotImplementedError("wavelet_in_unet needs model.use_other_channels: False (the reference passes "
+                                      "x_other=None in this mode, restoration.py:98-104)")
 
     # ------------------------------------------------------------------------------------------ core
     @torch.no_grad()
@@ -54,6 +57,8 @@ class DiffusiveRestoration:
         dev = df.device
         x = x.flatten(start_dim=0, end_dim=1) if x.ndim == 5 else x
         x = x.to(dev, torch.float32)
+        if getattr(self.config.data, "wavelet_in_unet", False):
+            return self._restore_batch_wavelet_in_unet(x, r, noise)
         cond01 = x[:, :3].contiguous()
         x_cond = dwt4x4(cond01, pre_2xm1=True)            # DWT(data_transform(cond))
         x_gt = dwt4x4(x[:, 3:].contiguous(), pre_2xm1=True)
@@ -93,6 +98,29 @@ class DiffusiveRestoration:
             if wd is not None:
                 out["all_wdnet"] = wd
         return out
+
+    def _restore_batch_wavelet_in_unet(self, x, r, noise):
+        """restoration.py:73-135 with data.wavelet_in_unet: the sampler runs in the PIXEL domain on patch_size crops
+        (:171-172), the network applies the DWT / IWT itself at every step (unet.py:349-350,393-394), no x_other, no
+        transform outside the loop (:87,:123)."""
+        df, cfgm = self.diffusion, self.config.model
+        dev = df.device
+        x_all = 2 * x - 1.0                                  # data_transform, restoration.py:74
+        x_cond = x_all[:, :3].contiguous()
+        p_size = self.config.data.patch_size
+        h_list, w_list = self.overlapping_grid_indices(x_cond, output_size=p_size, r=r)
+        corners = [(i, j) for i in h_list for j in w_list]
+        if noise is None:
+            noise = torch.randn((x_cond.shape[0], cfgm.pred_channels, x_cond.shape[2], x_cond.shape[3]), device=dev)
+        skip = self.config.diffusion.num_diffusion_timesteps // self.args.sampling_timesteps
+        seq = range(0, self.config.diffusion.num_diffusion_timesteps, skip)
+        net = df.model.module if hasattr(df.model, "module") else df.model
+        from .sampler import DdimSampler
+        sampler = DdimSampler(net.engine(), max_patches=getattr(self.args, "max_patches", None))
+        xs_hist, x0_hist = sampler.sample(noise, x_cond, None, seq, df.betas, corners, p_size)
+        latent = x0_hist[-5]                                # restoration.py:108
+        return {"latent": latent, "output": torch.clamp((latent + 1.0) / 2.0, 0.0, 1.0),
+                "cond": torch.clamp((x_cond + 1.0) / 2.0, 0.0, 1.0)}
 
     # ------------------------------------------------------------------------------------------ reference API
     def restore(self, val_loader, validation='snow', r=None):

@@ -47,8 +47,8 @@ class DdimSampler:
         if eta != 0.0:
             raise NotImplementedError("only eta = 0 (deterministic DDIM) is implemented; the reference never "
                                       "passes another value (ddm_wavelet.py:302)")
-        if p_size != eng.R:
-            raise ValueError(f"patch size {p_size} != UNet resolution {eng.R}")
+        if p_size != eng.patch:
+            raise ValueError(f"patch size {p_size} != the engine's patch side {eng.patch}")
         dev = eng.device
         x = x.to(dev, torch.float32).contiguous()
         x_cond = x_cond.to(dev, torch.float32).contiguous()
@@ -68,7 +68,7 @@ class DdimSampler:
         nh = S if keep_history else 1
         xs_hist = torch.empty((nh, B, Cp, h, w), dtype=torch.float32, device=dev)
         x0_hist = torch.empty((nh, B, Cp, h, w), dtype=torch.float32, device=dev)
-        eps = torch.empty((P, eng.out_ch, eng.R, eng.R), dtype=torch.float32, device=dev)
+        eps = torch.empty((P, eng.out_ch, eng.patch, eng.patch), dtype=torch.float32, device=dev)
         chunk = min(self.max_patches, P)
         xin = torch.empty((chunk, eng.R, eng.R, eng.cin_pad), dtype=eng.dtype, device=dev)
         xt = x

@@ -33,7 +33,7 @@ def _engine_of(model):
 def generalized_steps(x, x_cond, seq, model, b, eta=0.):
     """utils/sampling.py:23-44: whole-image DDIM; the image must be exactly the UNet resolution."""
     eng = _engine_of(model)
-    return DdimSampler(eng).sample_lists(x, x_cond, None, seq, b, [(0, 0)], eng.R, eta=eta)
+    return DdimSampler(eng).sample_lists(x, x_cond, None, seq, b, [(0, 0)], eng.patch, eta=eta)
 
 
 def generalized_steps_overlapping(x, x_cond, seq, model, b, eta=0., corners=None, p_size=None, manual_batching=True,

@@ -123,9 +123,14 @@ class DiffusionUNet(nn.Module):
         self.use_window = config.data.use_window
         self.window_size = config.data.window_size
         self.use_wavelet_in_unet = config.data.wavelet_in_unet
-        if self.use_window or self.use_wavelet_in_unet:
-            raise NotImplementedError("use_window / wavelet_in_unet UNet variants are not implemented "
+        if self.use_window:
+            raise NotImplementedError("the use_window UNet variant is not implemented "
                                       "(unused by raindrop_wavelet.yml; SURVEY.md 8f-4)")
+        if self.use_wavelet_in_unet:
+            # models/unet.py:203-206 -- created first, as in the reference (module order = state-dict / RNG order)
+            from .wavelet import WaveletTransform
+            self.wavelet_dec = WaveletTransform(scale=2, dec=True)
+            self.wavelet_rec = WaveletTransform(scale=2, dec=False)
         m = config.model
         ch, out_ch, ch_mult = m.ch, m.out_ch, tuple(m.ch_mult)
         in_channels = _engine.unet_in_channels(config)
@@ -211,7 +216,9 @@ class DiffusionUNet(nn.Module):
         return eng
 
     def forward(self, x, t):
-        assert x.shape[2] == x.shape[3] == self.resolution
+        # wavelet_in_unet: pixel-domain [P, 6, 4R, 4R] in, [P, 3, 4R, 4R] out (the reference asserts after its DWT, :351)
+        side = self.resolution * (4 if self.use_wavelet_in_unet else 1)
+        assert x.shape[2] == x.shape[3] == side
         if torch.is_grad_enabled() and self.training:
             return self._forward_autograd(x, t)
         return self.engine().forward(x, t)
@@ -219,6 +226,8 @@ class DiffusionUNet(nn.Module):
     # ------------------------------------------------------------------------------------------ training path
     def _forward_autograd(self, x, t):
         """Differentiable PyTorch definition (models/unet.py:353-389) -- training only, see module docstring."""
+        if self.use_wavelet_in_unet:  # all_wavlet_dec, models/unet.py:338-344
+            x = torch.cat([self.wavelet_dec(x[:, :3].contiguous()), self.wavelet_dec(x[:, 3:].contiguous())], dim=1)
         temb = get_timestep_embedding(t, self.ch)
         temb = self.temb.dense[1](nonlinearity(self.temb.dense[0](temb)))
         hs = [self.conv_in(x)]
@@ -238,4 +247,5 @@ class DiffusionUNet(nn.Module):
                     h = self.up[i_level].attn[i_block](h)
             if i_level != 0:
                 h = self.up[i_level].upsample(h)
-        return self.conv_out(nonlinearity(self.norm_out(h)))
+        h = self.conv_out(nonlinearity(self.norm_out(h)))
+        return self.wavelet_rec(h) if self.use_wavelet_in_unet else h
