@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--ddim-steps", type=int, default=DDIM_STEPS)
     ap.add_argument("--max-patches", type=int, default=64)
+    ap.add_argument("--wavelet-in-unet", action="store_true",
+                    help="NOT the BASELINE config: data.wavelet_in_unet (DWT / IWT inside the network at every DDIM step, "
+                         "pixel-domain sampler, out_ch 48); the line is labelled accordingly")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -108,11 +111,14 @@ def synth_inputs(batch, rank, device=None, pinned=False):
     return x, noise
 
 
-def make_cfg(precision, device):
+def make_cfg(precision, device, wavelet_in_unet=False):
     from wavedm_b200.configs import default_config
     cfg = default_config()
     cfg.device = device
     cfg.model.engine_precision = precision
+    if wavelet_in_unet:  # the only self-consistent setting of this mode
+        cfg.data.wavelet_in_unet = True
+        cfg.model.use_other_channels, cfg.model.in_channels, cfg.model.out_ch = False, 93, 48
     return cfg
 
 
@@ -187,6 +193,13 @@ def run_reference_arm(args):
 
 
 def workload_config(args, torch_version):
+    if getattr(args, "wavelet_in_unet", False):
+        return {"workload": f"NOT a BASELINE config -- data.wavelet_in_unet variant: batch {args.batch}/GPU, 256x256, "
+                            f"{args.ddim_steps} DDIM steps, {args.precision} UNet with the DWT (2x3 ch) and IWT (48 ch) inside "
+                            f"every step, pixel-domain sampler (1 256x256 patch/image), seed-61 default-init weights",
+                "global_batch": args.batch * args.gpus, "images_per_gpu": args.batch, "ddim_steps": args.ddim_steps,
+                "l2": "inputs+activations per step far exceed L2 (126 MB); weights 313 MB bf16", "torch": torch_version,
+                "hfrm": "not part of this mode (x_other = None, restoration.py:98-104)"}
     return {"workload": f"BASELINE.json configs[2]: batch {args.batch}/GPU, 256x256, {args.ddim_steps} DDIM steps, "
                         f"{args.precision} UNet (1 64x64 wavelet patch/image), raindrop_wavelet.yml, seed-61 default-init weights",
             "global_batch": args.batch * args.gpus, "images_per_gpu": args.batch, "ddim_steps": args.ddim_steps,
@@ -253,7 +266,7 @@ def main():
     except Exception:
         pass
 
-    cfg = make_cfg(args.precision, dev)
+    cfg = make_cfg(args.precision, dev, args.wavelet_in_unet)
     restorer = build_restorer(cfg, dev, sampling_timesteps=args.ddim_steps, max_patches=args.max_patches, seed=SEED,
                               broadcast=world > 1)
     lib = _lib.load()
@@ -262,7 +275,14 @@ def main():
     x_pin, noise_pin = synth_inputs(B, rank, pinned=True)
     x_gt_hf = None
 
+    if args.wavelet_in_unet:  # the sampler runs in the pixel domain: the initial noise is image-sized
+        g = torch.Generator().manual_seed(SEED + 100 + rank)
+        noise_pin = torch.randn(B, 3, H, W, generator=g).pin_memory()
+        noise_dev = noise_pin.to(dev)
+
     def step_device():
+        if args.wavelet_in_unet:
+            return restorer.restore_batch(x_dev, r=16, noise=noise_dev)["output"]
         xo = restorer.diffusion.wavelet_dec(2 * x_dev[:, 3:].contiguous() - 1.0)[:, 3:].contiguous()
         res = restorer.restore_batch(x_dev, r=16, noise=noise_dev, x_other=xo)
         return res["output"]
@@ -282,8 +302,11 @@ def main():
     def step_e2e():
         xh = x_pin.to(dev, non_blocking=True)
         nh = noise_pin.to(dev, non_blocking=True)
-        xo = restorer.diffusion.wavelet_dec(2 * xh[:, 3:].contiguous() - 1.0)[:, 3:].contiguous()
-        out = restorer.restore_batch(xh, r=16, noise=nh, x_other=xo)["output"]
+        if args.wavelet_in_unet:
+            out = restorer.restore_batch(xh, r=16, noise=nh)["output"]
+        else:
+            xo = restorer.diffusion.wavelet_dec(2 * xh[:, 3:].contiguous() - 1.0)[:, 3:].contiguous()
+            out = restorer.restore_batch(xh, r=16, noise=nh, x_other=xo)["output"]
         if world > 1:
             dist.gather(out, gathered, dst=0)
         out_pin.copy_(out, non_blocking=True)  # pinned destination; the timed region ends with a device synchronize
@@ -361,7 +384,7 @@ def main():
     if rank == 0:
         rdwt = dwt_roofline(dev, peaks["hbm_gbs"])
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and not args.wavelet_in_unet:
             cpu = cpu_baseline(args.cpu_sample_seconds, os.cpu_count() or 1)
         out = {"metric": "restored images/sec @256x256, 50-step DDIM", "value": value, "unit": "images/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

@@ -50,6 +50,37 @@ def main():
                 gbs = bytes_per / ms / 1e6
                 print(f"{kind} {name:6s} B={B} {H}x{W} nbuf={nbuf}: {ms*1e3:8.1f} us  {gbs:8.1f} GB/s  "
                       f"{gbs/peak:.3f} of measured peak {peak}")
+    # wavelet_in_unet per-step kernels: fused crop + DWT + concat + NHWC(bf16, 128 ch) gather, and the IWT of the NHWC result
+    P, R = 128, 64
+    nbuf = 4
+    srcs = [(torch.randn(P, 3, 4 * R, 4 * R, device=dev), torch.randn(P, 3, 4 * R, 4 * R, device=dev)) for _ in range(nbuf)]
+    outs = [torch.empty(P, R, R, 128, device=dev, dtype=torch.bfloat16) for _ in range(nbuf)]
+    pats = torch.zeros(P, 3, dtype=torch.int32, device=dev)
+    pats[:, 0] = torch.arange(P, dtype=torch.int32, device=dev)
+    ys = [torch.randn(P, R, R, 64, device=dev) for _ in range(nbuf)]
+    xo = [torch.empty(P, 3, 4 * R, 4 * R, device=dev) for _ in range(nbuf)]
+    st = torch.cuda.current_stream().cuda_stream
+    cases = {
+        "dwt_gather (2x3ch fp32 -> 96(+32 pad)ch bf16 NHWC)":
+            (lambda i: lib.wdm_gather_patches_dwt(srcs[i % nbuf][0].data_ptr(), srcs[i % nbuf][1].data_ptr(), 2, P, 4 * R, 4 * R,
+                                                  pats.data_ptr(), P, R, 128, outs[i % nbuf].data_ptr(), 1, st),
+             P * (6 * 16 * R * R * 4 + R * R * 128 * 2)),
+        "iwt_nhwc (48 of 64 fp32 columns -> 3ch fp32 NCHW)":
+            (lambda i: lib.wdm_iwt4x4_nhwc(ys[i % nbuf].data_ptr(), 64, P, R, xo[i % nbuf].data_ptr(), st),
+             P * (R * R * 48 * 4 + 3 * 16 * R * R * 4)),
+    }
+    for name, (fn, nbytes) in cases.items():
+        for i in range(5):
+            assert fn(i) == 0
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(40):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 40
+        print(f"{name} P={P}: {ms*1e3:8.1f} us  {nbytes/ms/1e6:8.1f} GB/s algorithmic  {nbytes/ms/1e6/peak:.3f} of measured peak")
     # torch copy for calibration on this box
     a = torch.empty(1 << 28, device=dev)
     b = torch.empty(1 << 28, device=dev)

@@ -163,15 +163,16 @@ template <typename TO>
 __global__ void __launch_bounds__(384) dwt_gather_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
                                                         int nsrc, int H, int W, const int* __restrict__ patches, int R,
                                                         int Cpad, TO* __restrict__ out) {
+    // staging tile [R][Cpad] in 32-bit words with an ODD row pitch: the sub-band scatter (fixed channel, consecutive j)
+    // and the row-contiguous copy-out are both bank-conflict free
     extern __shared__ __align__(16) unsigned char smem_dg[];
-    TO* tile = reinterpret_cast<TO*>(smem_dg);  // [R][Cpad]
+    constexpr int kPerWord = 4 / (int)sizeof(TO);  // 1 (fp32) or 2 (bf16) channels per word
+    uint32_t* tile = reinterpret_cast<uint32_t*>(smem_dg);
+    const int wpr = Cpad / kPerWord;  // words per output pixel
+    const int pitch = wpr | 1;
     const int i = blockIdx.x, pi = blockIdx.y;
     const int img = patches[pi * 3], hi = patches[pi * 3 + 1], wi = patches[pi * 3 + 2];
     const int nplanes = nsrc * 3;
-    for (int e = threadIdx.x; e < R * Cpad; e += blockDim.x) {
-        const int c = e % Cpad;
-        if (c >= nplanes * 16) tile[e] = TO(0.f);
-    }
     for (int u = threadIdx.x; u < nplanes * R; u += blockDim.x) {
         const int plane = u / R, j = u - plane * R;
         const int sidx = plane / 3, g = plane - 3 * sidx;
@@ -190,24 +191,46 @@ __global__ void __launch_bounds__(384) dwt_gather_kernel(const float* __restrict
         }
         float o[16];
         wht16_fwd(v, o);
+        TO* row = reinterpret_cast<TO*>(tile + j * pitch);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) tile[j * Cpad + sidx * 48 + 3 * k + g] = TO(o[k]);
+        for (int k = 0; k < 16; ++k) row[sidx * 48 + 3 * k + g] = TO(o[k]);
     }
     __syncthreads();
-    TO* dst = out + ((long long)pi * R + i) * R * Cpad;
-    const int n16 = R * Cpad * (int)sizeof(TO) / 16;
-    for (int e = threadIdx.x; e < n16; e += blockDim.x)
-        reinterpret_cast<uint4*>(dst)[e] = reinterpret_cast<const uint4*>(tile)[e];
+    uint4* dst = reinterpret_cast<uint4*>(out + ((long long)pi * R + i) * R * Cpad);
+    const int valid_words = nplanes * 16 / kPerWord;  // channels >= nplanes*16 are zero padding
+    const int qpr = wpr >> 2;                         // 16-byte units per output pixel (Cpad % 8 == 0)
+    for (int e = threadIdx.x; e < R * qpr; e += blockDim.x) {
+        const int j = e / qpr, cw = (e - j * qpr) * 4;
+        const uint32_t* t = tile + j * pitch + cw;
+        uint4 q;
+        q.x = cw + 0 < valid_words ? t[0] : 0u, q.y = cw + 1 < valid_words ? t[1] : 0u;
+        q.z = cw + 2 < valid_words ? t[2] : 0u, q.w = cw + 3 < valid_words ? t[3] : 0u;
+        dst[e] = q;
+    }
 }
 
 __global__ void __launch_bounds__(192) iwt_nhwc_kernel(const float* __restrict__ y, int ld, int R, float* __restrict__ x) {
+    // the row of R pixels x ld floats is staged with coalesced 16-byte loads; odd pitch -> the stride-3 sub-band reads of
+    // consecutive pixels fall into different banks
+    extern __shared__ __align__(16) unsigned char smem_in[];
+    float* tile = reinterpret_cast<float*>(smem_in);
+    const int pitch = ld | 1;
     const int i = blockIdx.x, pi = blockIdx.y;
+    const float4* src4 = reinterpret_cast<const float4*>(y + ((long long)pi * R + i) * R * ld);
+    const int ld4 = ld >> 2;
+    for (int e = threadIdx.x; e < R * 12; e += blockDim.x) {  // 12 float4 = the 48 sub-band columns of a pixel
+        const int j = e / 12, c4 = e - j * 12;
+        const float4 q = __ldg(src4 + j * ld4 + c4);
+        float* t = tile + j * pitch + c4 * 4;
+        t[0] = q.x, t[1] = q.y, t[2] = q.z, t[3] = q.w;
+    }
+    __syncthreads();
     for (int u = threadIdx.x; u < 3 * R; u += blockDim.x) {
         const int g = u / R, j = u - g * R;
-        const float* src = y + (((long long)pi * R + i) * R + j) * ld + g;
+        const float* t = tile + j * pitch + g;
         float in[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) in[k] = __ldg(src + 3 * k);
+        for (int k = 0; k < 16; ++k) in[k] = t[3 * k];
         float v[4][4];
         wht16_inv(in, v);
         const int Wp = 4 * R;
@@ -510,8 +533,8 @@ int launch_dwt_gather(const float* src0, const float* src1, int nsrc, int B, int
     if (!src0 || nsrc < 1 || nsrc > 2 || (nsrc == 2 && !src1) || !patches || !out) return WDM_ERR_BAD_ARG;
     if (R <= 0 || 4 * R > H || 4 * R > W || Cpad < nsrc * 48 || (Cpad % 8) || B <= 0) return WDM_ERR_BAD_SHAPE;
     if (!wdm_aligned(out, 16)) return WDM_ERR_BAD_ALIGN;
-    const size_t es = out_dtype == 0 ? 4 : 2;
-    const size_t smem = (size_t)R * Cpad * es;
+    const size_t wpr = out_dtype == 0 ? (size_t)Cpad : (size_t)Cpad / 2;
+    const size_t smem = (size_t)R * (wpr | 1) * 4;
     if (smem > 96 * 1024) return WDM_ERR_BAD_SHAPE;
     dim3 grid(R, P);
     if (out_dtype == 0) {
@@ -527,9 +550,12 @@ int launch_dwt_gather(const float* src0, const float* src1, int nsrc, int B, int
 
 int launch_iwt_nhwc(const float* y, int ld, int P, int R, float* x, cudaStream_t s) {
     if (P <= 0) return WDM_OK;
-    if (!y || !x || ld < 48 || R <= 0) return WDM_ERR_BAD_ARG;
-    if (!wdm_aligned(x, 16)) return WDM_ERR_BAD_ALIGN;
-    iwt_nhwc_kernel<<<dim3(R, P), 192, 0, s>>>(y, ld, R, x);
+    if (!y || !x || ld < 48 || (ld & 3) || R <= 0) return WDM_ERR_BAD_ARG;
+    if (!wdm_aligned(x, 16) || !wdm_aligned(y, 16)) return WDM_ERR_BAD_ALIGN;
+    const size_t smem = (size_t)R * (ld | 1) * sizeof(float);
+    if (smem > 96 * 1024) return WDM_ERR_BAD_SHAPE;
+    cudaFuncSetAttribute(iwt_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    iwt_nhwc_kernel<<<dim3(R, P), 192, smem, s>>>(y, ld, R, x);
     return wdm_launch_status();
 }
 }  // namespace wdm
