@@ -104,16 +104,22 @@ constexpr int kSmemMax = 232448;  // 227 KiB per CTA
 
 // MT = M-tiles (128 rows each) that share one B tile per k-block: MT = 2 halves the weight traffic per FLOP
 // (the kernel is L2->SM bandwidth bound) at the price of TMEM: 2 accumulators per buffer.
-template <int BN, int MT>
+// HALO (3x3 stride-1 convolutions, Cout = 128 tiles): the three dy taps of a (dx, 64-channel chunk) read the SAME
+// activation rows shifted by whole image rows, so ONE box of MT*rows+2 image rows is loaded per (dx, chunk) and the
+// dy taps address it at row offsets (whole 1024-byte swizzle atoms): A-operand traffic out of L2 halves (6 instead of 12
+// image rows per three taps at W = 64). A macro-stage = that halo box (<= 48 KiB) + the three weight tiles (3 x 16 KiB).
+constexpr int kHaloABytes = 49152;
+template <int BN, int MT, bool HALO = false>
 struct Cfg {
     static constexpr int kBBytes = BN * kBK * 2;
-    static constexpr int kStage = MT * kABytes + kBBytes;
+    static constexpr int kStage = HALO ? kHaloABytes + 3 * kBBytes : MT * kABytes + kBBytes;
     static constexpr int kTail = tail_bytes(BN, MT);
     static constexpr int kStages = (kSmemMax - 1024 - kTail) / kStage < kSmemBudget / kStage ? (kSmemMax - 1024 - kTail) / kStage
                                                                                              : kSmemBudget / kStage;
     static constexpr int kBufs = (2 * MT * BN <= 512) ? 2 : 1;          // accumulator buffers in TMEM
     static constexpr int kTmemCols = kBufs * MT * BN;                   // 512 / 256 / 128: powers of two >= 32
     static constexpr int kSmem = kStages * kStage + 1024 /*alignment slack*/ + kTail;
+    static_assert(!HALO || (2 * (MT * kABytes + kBBytes) <= kStage), "a macro-stage also holds two plain k-blocks (1x1 tails)");
 };
 
 // Epilogue of one super-tile (MT accumulators of 128 rows x BN columns). Thread `row` owns one TMEM lane of every
@@ -471,12 +477,12 @@ __device__ __forceinline__ void epilogue_softmax(const TcArgs& a, uint32_t tacc,
     }
 }
 
-template <int BN, int MT, bool SWAP = false>
+template <int BN, int MT, bool SWAP = false, bool HALO = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcArgs a) {
-    using C = Cfg<BN, MT>;
+    using C = Cfg<BN, MT, HALO>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStage);
@@ -525,7 +531,124 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int kblocks = 0;
     for (int g = 0; g < a.nseg; ++g) kblocks += a.seg_taps[g] * a.seg_kc[g];
 
-    if (warp == kWarpTma) {
+    if (HALO && warp == kWarpTma) {
+        // ------------------------------------------------------------------ TMA producer, halo macro-stages
+        // tmA0 carries the halo box {64 ch, W, MT*rows + 2, 1}; segments 1, 2 (1x1 shortcut tails) are plain k-blocks, two
+        // per macro-stage
+        const int W = a.Wout, rows = kBM / W;
+        const uint32_t halo_bytes = (uint32_t)(MT * rows + 2) * W * 128;
+        const int skc0 = a.seg_kc[0], ntail = a.nseg > 1 ? a.seg_kc[1] + (a.nseg > 2 ? a.seg_kc[2] : 0) : 0;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int st = tile / a.n_tiles, nt = tile - st * a.n_tiles;
+            int n_img[MT], cy0[MT];
+#pragma unroll
+            for (int h = 0; h < MT; ++h) {
+                const int m0 = (st * MT + h) * kBM;
+                n_img[h] = m0 / a.HWout;
+                cy0[h] = (m0 - n_img[h] * a.HWout) / W;
+            }
+            for (int kc = 0; kc < skc0; ++kc) {
+                for (int dx = 0; dx < 3; ++dx, ++it) {
+                    const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
+                    ptx::mbar_wait(&empty[s], ph ^ 1);
+                    if (lane == 0) {
+                        uint8_t* sa = smem + s * C::kStage;
+                        if (a.dbg == 1 || a.dbg == 9) {
+                            ptx::mbar_arrive(&full[s]);
+                        } else {
+                            ptx::mbar_arrive_expect_tx(&full[s], halo_bytes + 3 * C::kBBytes);
+                            ptx::tma_load_4d(sa, &tmA0, &full[s], kc * kBK, dx - a.pad, cy0[0] - a.pad, n_img[0]);
+#pragma unroll
+                            for (int dy = 0; dy < 3; ++dy)
+                                ptx::tma_load_2d(sa + kHaloABytes + dy * C::kBBytes, &tmB, &full[s],
+                                                 ((dy * 3 + dx) * skc0 + kc) * kBK, nt * BN);
+                        }
+                        if (it == 0) tc_trace(a, 3);
+                    }
+                    __syncwarp();
+                }
+            }
+            for (int t0 = 0; t0 < ntail; t0 += 2, ++it) {
+                const int nk = ntail - t0 >= 2 ? 2 : 1;
+                const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
+                ptx::mbar_wait(&empty[s], ph ^ 1);
+                if (lane == 0) {
+                    if (a.dbg == 1 || a.dbg == 9) {
+                        ptx::mbar_arrive(&full[s]);
+                    } else {
+                        ptx::mbar_arrive_expect_tx(&full[s], nk * (MT * kABytes + C::kBBytes));
+                        for (int j = 0; j < nk; ++j) {
+                            const int t = t0 + j;
+                            const bool second = t >= a.seg_kc[1];
+                            const CUtensorMap* tm = second ? &tmA2 : &tmA1;
+                            const int kc = second ? t - a.seg_kc[1] : t;
+                            uint8_t* base = smem + s * C::kStage + j * (MT * kABytes + C::kBBytes);
+#pragma unroll
+                            for (int h = 0; h < MT; ++h)
+                                ptx::tma_load_4d(base + h * kABytes, tm, &full[s], kc * kBK, 0, cy0[h], n_img[h]);
+                            ptx::tma_load_2d(base + MT * kABytes, &tmB, &full[s], (9 * skc0 + t) * kBK, nt * BN);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (HALO && warp == kWarpMma) {
+        // ------------------------------------------------------------------ MMA issuer, halo macro-stages
+        constexpr uint32_t idesc = make_idesc(kBM, BN);
+        const int W = a.Wout, rows = kBM / W;
+        const int skc0 = a.seg_kc[0], ntail = a.nseg > 1 ? a.seg_kc[1] + (a.nseg > 2 ? a.seg_kc[2] : 0) : 0;
+        const int nmain = 3 * skc0, nmacro = nmain + (ntail + 1) / 2;
+        uint32_t it = 0, tl = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+            const uint32_t as = tl % C::kBufs, aph = (tl / C::kBufs) & 1;
+            ptx::mbar_wait(&tempty[as], aph ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * (MT * BN);
+            for (int mi = 0; mi < nmacro; ++mi, ++it) {
+                const uint32_t s = it % C::kStages;
+                ptx::mbar_wait(&full[s], (it / C::kStages) & 1);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    if (it == 0) tc_trace(a, 4);
+                    const uint32_t sa = ptx::smem_u32(smem + s * C::kStage);
+                    if (a.dbg == 2) {
+                    } else if (mi < nmain) {
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint64_t db = make_smem_desc(sa + kHaloABytes + dy * C::kBBytes);
+#pragma unroll
+                            for (int k = 0; k < kBK / 16; ++k) {
+#pragma unroll
+                                for (int h = 0; h < MT; ++h)
+                                    ptx::umma_f16_ss(d_tmem + h * BN, make_smem_desc(sa + (dy + h * rows) * W * 128) + 2 * k,
+                                                     db + 2 * k, idesc, (mi | dy | k) ? 1u : 0u);
+                            }
+                        }
+                    } else {
+                        const int t0 = (mi - nmain) * 2, nk = ntail - t0 >= 2 ? 2 : 1;
+                        for (int j = 0; j < nk; ++j) {
+                            const uint32_t base = sa + j * (MT * kABytes + C::kBBytes);
+                            const uint64_t db = make_smem_desc(base + MT * kABytes);
+#pragma unroll
+                            for (int k = 0; k < kBK / 16; ++k) {
+#pragma unroll
+                                for (int h = 0; h < MT; ++h)
+                                    ptx::umma_f16_ss(d_tmem + h * BN, make_smem_desc(base + h * kABytes) + 2 * k, db + 2 * k, idesc, 1u);
+                            }
+                        }
+                    }
+                    ptx::umma_commit(&empty[s]);
+                    if (mi + 1 == nmacro) {
+                        ptx::umma_commit(&tfull[as]);
+                        if (tl < 2) tc_trace(a, 5 + tl);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == kWarpTma) {
         // ------------------------------------------------------------------ TMA producer
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -968,15 +1091,15 @@ int num_sms_tc() {
     return sms;
 }
 
-template <int BN, int MT, bool SWAP = false>
+template <int BN, int MT, bool SWAP = false, bool HALO = false>
 int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& A2, const CUtensorMap& B, const CUtensorMap& O,
               const TcArgs& a, cudaStream_t s) {
-    using C = Cfg<BN, MT>;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MT, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    using C = Cfg<BN, MT, HALO>;
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MT, SWAP, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     const int tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;
     const int grid = tiles < num_sms_tc() ? tiles : num_sms_tc();
-    e = wdm_launch_pdl(gemm_tc_kernel<BN, MT, SWAP>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, A2, B, O, a);
+    e = wdm_launch_pdl(gemm_tc_kernel<BN, MT, SWAP, HALO>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, A2, B, O, a);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     return wdm_launch_status();
 }
@@ -1107,6 +1230,18 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     }
     const int b_box_rows = use_pair ? BN / 2 : BN;
 
+    // halo macro-stages for the Cout = 128 3x3 stride-1 convolutions (Cfg<.., HALO>): needs two consecutive m-tiles of
+    // one patch per super-tile and a halo box of at most 48 KiB
+    static const int halo_enabled = []() {
+        const char* e = getenv("WDM_TC_HALO");
+        return e ? atoi(e) : 1;
+    }();
+    const int m_tiles_all = (p.M + kBM - 1) / kBM;
+    const bool use_halo = halo_enabled && !use_pair && BN == 128 && p.taps == 9 && p.stride == 1 && !subpix &&
+                          !p.b_batch_stride && !p.a_shared && !p.fuse_softmax && g.Nb == 1 && (HWout % (2 * kBM)) == 0 &&
+                          (2 * g.Hb + 2) * g.Wb * 128 <= kHaloABytes && (!p.C1 || p.tail_1x1) && g_force_mt != 1 &&
+                          pick_mt(m_tiles_all, p.N / BN, BN, true) == 2;
+
     CUtensorMap A0, A1, A2, B;
     auto make_a = [&](CUtensorMap* m, const void* src, int C, int ld) -> int {
         uint64_t dims[4] = {(uint64_t)C, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)npatch};
@@ -1116,7 +1251,16 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, src, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, es);
     };
-    int r = make_a(&A0, p.src0, p.C0, p.ld0);
+    int r;
+    if (use_halo) {
+        uint64_t dims[4] = {(uint64_t)p.C0, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)npatch};
+        uint64_t strides[3] = {(uint64_t)p.ld0 * 2, (uint64_t)p.Win * p.ld0 * 2, (uint64_t)p.Hin * p.Win * p.ld0 * 2};
+        uint32_t box[4] = {(uint32_t)kBK, (uint32_t)g.Wb, (uint32_t)(2 * g.Hb + 2), 1};
+        r = make_tmap(&A0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p.src0, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    } else {
+        r = make_a(&A0, p.src0, p.C0, p.ld0);
+    }
     if (r) return r < 0 ? WDM_ERR_UNSUPPORTED : wdm_cuda_error(r);
     if (p.C1) {
         r = make_a(&A1, p.src1, p.C1, p.ld1);
@@ -1221,6 +1365,8 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         if (use_pair)
             rc = BN == 128 ? (pair128x2 ? launch_pair<128, 2>(A0, A1, A2, B, O, a, s) : launch_pair<128>(A0, A1, A2, B, O, a, s))
                            : (pair192 ? launch_pair<192>(A0, A1, A2, B, O, a, s) : launch_pair<256>(A0, A1, A2, B, O, a, s));
+        else if (use_halo)
+            rc = launch_bn<128, 2, false, true>(A0, A1, A2, B, O, a, s);
         else
             rc = BN == 256 ? launch_bn<256, 1>(A0, A1, A2, B, O, a, s)
                            : (BN == 128 ? launch_bn<128, 2>(A0, A1, A2, B, O, a, s) : launch_bn<64, 2>(A0, A1, A2, B, O, a, s));
@@ -1243,6 +1389,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     const bool allow2 = !a.b_batched || (a.tiles_per_batch % 2 == 0);
     const int MT = g_force_mt ? (g_force_mt == 2 && allow2 && BN != 256 ? 2 : 1) : pick_mt(a.m_tiles, a.n_tiles, BN, allow2);
     if (BN == 256) return launch_bn<256, 1>(A0, A1, A2, B, O, a, s);
+    if (use_halo) return launch_bn<128, 2, false, true>(A0, A1, A2, B, O, a, s);
     if (BN == 128 && MT == 2) {
         // swap-AB (128 couts x 256 pixels per MMA) for the plain bf16 layouts; see epi_rows_swap
         static const int swap_enabled = []() {
