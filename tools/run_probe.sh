@@ -1,12 +1,10 @@
 #!/bin/bash
-# GPU-box driver (run through gpurun)
+# GPU-box driver (run through gpurun): ncu evidence for the committed state -> gpurun_out/ (keep it < 64 MiB)
 cd $GRAFT_REPO_ROOT
 O=gpurun_out/probe.log
 : > $O
-(timeout 900 python -m pytest tests/test_unet_gpu.py -m gpu -x -q 2>&1 | tail -8) >> $O
-timeout 100 python tools/tc_probe.py 2>&1 | grep "128->128" >> $O
-WDM_TC_HALO=0 timeout 100 python tools/tc_probe.py 2>&1 | grep "128->128" >> $O
-WDM_TC_DBG=9 timeout 100 python tools/tc_probe.py 2>&1 | grep "128->128" >> $O
-WDM_TC_DBG=1 timeout 100 python tools/tc_probe.py 2>&1 | grep "128->128" >> $O
-timeout 200 python tools/profile_unet.py --patches 64 --iters 5 --time 2>&1 | grep -v "^profile" >> $O
-cat $O
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 700 --csv --log-file gpurun_out/r01_v13_dram_unet_p64.csv python tools/profile_unet.py --patches 64 --iters 1 >> $O 2>&1
+timeout 400 ncu --set full --clock-control none -k regex:"gemm_tc|gn_apply" -s 133 -c 20 -o gpurun_out/r01_v13_full_a python tools/profile_unet.py --patches 64 --iters 1 >> $O 2>&1
+timeout 400 ncu --set full --clock-control none -k regex:"gemm_tc" -s 120 -c 14 -o gpurun_out/r01_v13_full_b python tools/profile_unet.py --patches 64 --iters 1 >> $O 2>&1
+tail -2 $O
+ls -la gpurun_out/ | tail -5
