@@ -235,7 +235,11 @@ __device__ __forceinline__ void epi_rows(const TcArgs& a, const CUtensorMap* tmO
             const int n = nt * BN + ch * 32;
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * a.alpha;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (a.alpha != 1.f) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= a.alpha;
+            }
             if (has_b) {
                 const float4* b4p = reinterpret_cast<const float4*>(sb + hh * kW + c * 32);
 #pragma unroll

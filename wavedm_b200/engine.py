@@ -232,6 +232,7 @@ class UNetEngine:
 
     # ------------------------------------------------------------------------------------------ profiling
     def profile(self, on: bool) -> None:
+        self._profiling = bool(on)  # event-bracketed launches cannot be captured into a CUDA graph
         _lib.check(self.lib.wdm_unet_profile_enable(self.handle, 1 if on else 0), "wdm_unet_profile_enable")
 
     def profile_read(self):
