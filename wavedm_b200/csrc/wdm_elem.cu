@@ -508,7 +508,36 @@ __global__ void pack_subpix_weight_kernel(const float* __restrict__ w, int Cout,
 
 }  // namespace
 
+// Pack-time products of two C x C fp32 matrices (the algebraic attention fusion in wdm_unet.cu): one thread per output,
+// fp32 FMA chain over c in ascending order (deterministic).  mode 0: out = X^T Y,  mode 1: out = X Y.
+__global__ void __launch_bounds__(256) matmul_cc_kernel(const float* __restrict__ X, const float* __restrict__ Y,
+                                                       float* __restrict__ out, int C, int mode) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, a = blockIdx.y;
+    if (b >= C) return;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(mode == 0 ? X[(long long)c * C + a] : X[(long long)a * C + c], Y[(long long)c * C + b], acc);
+    out[(long long)a * C + b] = acc;
+}
+// out[a] = sum_c (mode 0: X[c][a], mode 1: X[a][c]) * v[c] (+ add[a])
+__global__ void __launch_bounds__(256) matvec_c_kernel(const float* __restrict__ X, const float* __restrict__ v,
+                                                      const float* __restrict__ add, float* __restrict__ out, int C, int mode) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= C) return;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(mode == 0 ? X[(long long)c * C + a] : X[(long long)a * C + c], v[c], acc);
+    out[a] = acc + (add ? add[a] : 0.f);
+}
+
 // ================================================================================================ launchers
+int launch_matmul_cc(const float* X, const float* Y, float* out, int C, int mode, cudaStream_t s) {
+    matmul_cc_kernel<<<dim3((C + 255) / 256, C), 256, 0, s>>>(X, Y, out, C, mode);
+    return wdm_launch_status();
+}
+int launch_matvec_c(const float* X, const float* v, const float* add, float* out, int C, int mode, cudaStream_t s) {
+    matvec_c_kernel<<<(C + 255) / 256, 256, 0, s>>>(X, v, add, out, C, mode);
+    return wdm_launch_status();
+}
+
 int launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t s) {
     vec_add_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, out, n);
     return wdm_launch_status();

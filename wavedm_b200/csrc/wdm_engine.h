@@ -106,6 +106,9 @@ int launch_pack_conv_weight(const float* w, int Cout, int Cin, int taps, int Cin
                             long long ldk, long long k_off, cudaStream_t stream);
 
 int launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t stream);
+// pack-time C x C fp32 products: mode 0 out = X^T Y, mode 1 out = X Y; matvec: out = X^T v / X v (+ add)
+int launch_matmul_cc(const float* X, const float* Y, float* out, int C, int mode, cudaStream_t stream);
+int launch_matvec_c(const float* X, const float* v, const float* add, float* out, int C, int mode, cudaStream_t stream);
 // sub-pixel decomposition of (nearest x2 upsample -> 3x3 conv): [4 phases][Cout][4 taps][Cin] (see wdm_elem.cu)
 int launch_pack_subpix_weight(const float* w, int Cout, int Cin, void* out, int out_dtype, cudaStream_t stream);
 

@@ -51,6 +51,15 @@ struct AttnSpec {
     GnSpec norm;
     int q[2], k[2], v[2];
     ConvSpec qkv, proj;  // qkv: fused [3C][C]
+    // Algebraic fusion (bf16 tensor-core mode): softmax_j(q_i.k_j) only sees  h_i^T (Wq^T Wk) h_j + (Wk^T bq).h_j , and
+    // proj(P v) = P (h (Wp Wv)^T) + (Wp bv + bp)  because the rows of P sum to one. With G = Wk^T Wq, u = Wk^T bq,
+    // Wpv = Wp Wv, bo = Wp bv + bp (fp32 products at pack time, then bf16) the block is FOUR contractions --
+    // g = h G^T + u;  w^T = Wpv h^T;  P = softmax(g h^T C^-1/2);  out = P w + bo + x -- instead of five, with 40 % fewer
+    // FLOPs (no k, no separate proj_out).
+    void* gw = nullptr;     // [C][C] G
+    float* gb = nullptr;    // [C]    u
+    void* wpv = nullptr;    // [C][C] Wp Wv
+    float* bo = nullptr;    // [C]    Wp bv + bp
 };
 struct LevelSpec {
     std::vector<ResSpec> blocks;
@@ -362,6 +371,28 @@ int pack_model(wdm_unet* net, const float* flat, cudaStream_t s, size_t* total) 
             }
         }
         pack_conv(a.proj, C);
+        if (dt == DT_BF16) {
+            a.gw = take((size_t)C * C * es);
+            a.gb = reinterpret_cast<float*>(take((size_t)C * 4));
+            a.wpv = take((size_t)C * C * es);
+            a.bo = reinterpret_cast<float*>(take((size_t)C * 4));
+            float* tmp = reinterpret_cast<float*>(take((size_t)C * C * 4));  // fp32 product before the bf16 rounding
+            if (fill && st == WDM_OK) {
+                const float* Wq = flat + m.params[a.q[0]].off;
+                const float* bq = flat + m.params[a.q[1]].off;
+                const float* Wk = flat + m.params[a.k[0]].off;
+                const float* Wv = flat + m.params[a.v[0]].off;
+                const float* bv = flat + m.params[a.v[1]].off;
+                const float* Wp = flat + m.params[a.proj.w].off;
+                const float* bp = flat + m.params[a.proj.b].off;
+                st = launch_matmul_cc(Wk, Wq, tmp, C, 0, s);                                        // G = Wk^T Wq
+                if (st == WDM_OK) st = launch_pack_conv_weight(tmp, C, C, 1, C, a.gw, dt, C, 0, s);
+                if (st == WDM_OK) st = launch_matvec_c(Wk, bq, nullptr, a.gb, C, 0, s);              // u = Wk^T bq
+                if (st == WDM_OK) st = launch_matmul_cc(Wp, Wv, tmp, C, 1, s);                      // Wpv = Wp Wv
+                if (st == WDM_OK) st = launch_pack_conv_weight(tmp, C, C, 1, C, a.wpv, dt, C, 0, s);
+                if (st == WDM_OK) st = launch_matvec_c(Wp, bv, bp, a.bo, C, 1, s);                  // bo = Wp bv + bp
+            }
+        }
     };
 
     const int g = k_granule(dt);
@@ -643,32 +674,43 @@ Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a, int G) {
     // on groups of G*L rows and the softmax is block-diagonal (cross-patch scores are masked to zero probability).
     const int C = a.C, L = x.H * x.W, P = c.P, Lg = G * L, Hg = G * x.H;
     const size_t es = 2;
+    static const int fused_enabled = []() {
+        const char* e = getenv("WDM_ATTN_FUSED");
+        return e ? atoi(e) : 1;
+    }();
+    const bool fused = fused_enabled && a.gw && a.wpv;  // the four-contraction form (see AttnSpec)
     Act n = gn_op(c, x, nullptr, a.norm, 0);
     GemmParams p;
-    // qk
-    Act qk = new_act(c, x.H, x.W, 2 * C);
+    // fused: g = n G^T + u  [P*L][C];  unfused: qk = n Wqk^T + b  [P*L][2C]
+    const int ldq = fused ? C : 2 * C;
+    Act qk = new_act(c, x.H, x.W, ldq);
     memset(&p, 0, sizeof p);
     p.src0 = n.p, p.C0 = C, p.ld0 = C, p.Hin = p.Hout = x.H, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
-    p.B = a.qkv.pw, p.ldb = C, p.b_layout = BL_NK, p.M = P * L, p.N = 2 * C, p.K = C, p.alpha = 1.f, p.bias = a.qkv.pb;
-    p.out = qk.p, p.ldo = 2 * C, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
+    p.B = fused ? a.gw : a.qkv.pw, p.ldb = C, p.b_layout = BL_NK, p.M = P * L, p.N = ldq, p.K = C, p.alpha = 1.f;
+    p.bias = fused ? a.gb : a.qkv.pb;
+    p.out = qk.p, p.ldo = ldq, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
     run_gemm(c, p);
-    // vT
+    // vT = Wv n^T (fused: w^T = (Wp Wv) n^T)   [P][C][L]: A = weights shared by all patches, B = n per patch
     void* vT = c.ar->alloc((size_t)P * C * L * es);
     if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
     memset(&p, 0, sizeof p);
-    p.src0 = (char*)a.qkv.pw + (size_t)2 * C * C * es, p.C0 = C, p.ld0 = C, p.a_shared = 1;
+    p.src0 = fused ? a.wpv : (void*)((char*)a.qkv.pw + (size_t)2 * C * C * es), p.C0 = C, p.ld0 = C, p.a_shared = 1;
     p.Hin = p.Hout = C / 128, p.Win = p.Wout = 128, p.taps = 1, p.stride = 1;
     p.B = n.p, p.ldb = C, p.b_batch_stride = (long long)Lg * C, p.b_layout = BL_NK;
     p.M = (P / G) * C, p.N = Lg, p.K = C, p.alpha = 1.f;
     p.out = vT, p.ldo = Lg, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
     run_gemm(c, p);
-    free_act(c, n);
-    // S -> softmax fused in the score GEMM's epilogue (probabilities straight to bf16; the fp32 scores stay in TMEM)
+    // S -> softmax fused in the score GEMM's epilogue (probabilities straight to bf16; the fp32 scores stay in TMEM).
+    // fused: keys = n itself (K-major rows of the normalised input), unfused: the k half of qk
     void* Pm = c.ar->alloc((size_t)P * L * Lg * es);
     if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
     memset(&p, 0, sizeof p);
-    p.src0 = qk.p, p.C0 = C, p.ld0 = 2 * C, p.Hin = p.Hout = Hg, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
-    p.B = (char*)qk.p + (size_t)C * es, p.b_batch_stride = (long long)Lg * 2 * C, p.ldb = 2 * C, p.b_layout = BL_NK;
+    p.src0 = qk.p, p.C0 = C, p.ld0 = ldq, p.Hin = p.Hout = Hg, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
+    if (fused)
+        p.B = n.p, p.b_batch_stride = (long long)Lg * C, p.ldb = C;
+    else
+        p.B = (char*)qk.p + (size_t)C * es, p.b_batch_stride = (long long)Lg * 2 * C, p.ldb = 2 * C;
+    p.b_layout = BL_NK;
     p.M = P * L, p.N = Lg, p.K = C, p.alpha = (float)(1.0 / sqrt((double)C));
     p.out = Pm, p.ldo = Lg, p.a_dtype = p.b_dtype = DT_BF16, p.out_dtype = DT_BF16;
     p.fuse_softmax = 1, p.softmax_seg = G > 1 ? L : 0;
@@ -684,17 +726,27 @@ Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a, int G) {
         if (!c.dry() && c.st == WDM_OK) c.fail(launch_softmax_rows(S, P * L, Lg, Pm, DT_BF16, c.s, G > 1 ? L : 0));
     }
     free_act(c, qk);
-    // O
+    free_act(c, n);
+    // O = Pm vT^T + b_v  (fused: the block output  Pm w + bo + x  with the GroupNorm side-car of the next block)
     Act O = new_act(c, x.H, x.W, C);
     memset(&p, 0, sizeof p);
     p.src0 = Pm, p.C0 = Lg, p.ld0 = Lg, p.Hin = p.Hout = Hg, p.Win = p.Wout = x.W, p.taps = 1, p.stride = 1;
     p.B = vT, p.b_batch_stride = (long long)C * Lg, p.ldb = Lg, p.b_layout = BL_NK;
-    p.M = P * L, p.N = C, p.K = Lg, p.alpha = 1.f, p.bias = a.qkv.pb + 2 * C;
+    p.M = P * L, p.N = C, p.K = Lg, p.alpha = 1.f, p.bias = fused ? a.bo : a.qkv.pb + 2 * C;
     p.out = O.p, p.ldo = C, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
+    if (fused) {
+        p.residual = x.p, p.ldr = x.C;
+        if ((p.M % 32) == 0 && (Hg * x.W) % 32 == 0) {
+            O.stats = reinterpret_cast<float*>(c.ar->alloc((size_t)(p.M / 32) * (p.N / 4) * 2 * sizeof(float)));
+            if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
+            p.stats_out = O.stats;
+        }
+    }
     run_gemm(c, p);
     if (S) c.ar->free(S);
     c.ar->free(Pm);
     c.ar->free(vT);
+    if (fused) return O;
     Act out = conv_op(c, O, nullptr, a.proj, 1, 0, nullptr, &x, true);
     free_act(c, O);
     return out;
