@@ -72,6 +72,8 @@ class _StepGraph:
 class DdimSampler:
     #: patch counts up to this run the per-step (gather, UNet) pair as a replayed CUDA graph
     GRAPH_MAX_PATCHES = 16
+    #: captured graphs (with their persistent buffers) kept per engine, least recently used evicted
+    GRAPH_CACHE_ENTRIES = 4
 
     def __init__(self, engine: UNetEngine, max_patches: Optional[int] = None, use_graph: Optional[bool] = None):
         self.engine = engine
@@ -135,11 +137,14 @@ class DdimSampler:
         eng = self.engine
         key = (tuple(x.shape), tuple(x_cond.shape), None if x_other is None else tuple(x_other.shape), patches.shape[0])
         cache = eng.__dict__.setdefault("_step_graphs", {})
-        sg = cache.get(key)
+        sg = cache.pop(key, None)
         if sg is None:
-            sg = cache[key] = _StepGraph(eng, x_cond, x, x_other, patches)
+            while len(cache) >= self.GRAPH_CACHE_ENTRIES:   # least recently used shape goes first
+                cache.pop(next(iter(cache)))
+            sg = _StepGraph(eng, x_cond, x, x_other, patches)
         else:
             sg.load(x_cond, x, x_other, patches)
+        cache[key] = sg
         for k, (i_t, j_t) in enumerate(zip(reversed(seq), reversed(seq_next))):
             sg.t.copy_(tvals[k:k + 1])
             sg.graph.replay()
