@@ -1,10 +1,9 @@
 #!/bin/bash
-# GPU-box driver (run through gpurun): the round-end sequence the driver runs, plus the event span table -> gpurun_out/
+# GPU-box driver (run through gpurun)
 cd $GRAFT_REPO_ROOT
 O=gpurun_out/probe.log
 : > $O
-(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4) >> $O
-(timeout 120 python __graft_entry__.py smoke 2>&1 | tail -1) >> $O
-timeout 400 python bench.py > gpurun_out/bench_v14.json 2>> $O
-timeout 200 python tools/profile_unet.py --patches 64 --iters 5 --time --spans > gpurun_out/r01_v14_spans.txt 2>&1
-tail -3 $O
+for dbg in 0 8 6 7 5; do
+WDM_TC_DBG=$dbg timeout 100 python tools/tc_probe.py 2>&1 | grep "128->128.*full=1\|512->512.*taps=1 full=1" >> $O
+done
+cat $O
