@@ -70,6 +70,11 @@ WDM_API long long wdm_launch_counter(void);
 
 WDM_API int wdm_dwt4x4_fwd(const float* x, float* y, int n, int H, int W, int flags, void* stream);
 WDM_API int wdm_iwt4x4_fwd(const float* y, float* x, int n, int h, int w, int flags, void* stream);
+/* models/restoration.py:111-135 in one kernel: IWT of cat([lo[:, :Clo], hi-bands]) (+ WDM_IWT_POST_CLAMP) without the
+ * concatenated tensor. lo: [n, >=Clo.. exactly Clo channels used, tensor has Clo channels]; hi: [n, Chi, h, w] with
+ * Chi == 48 (full wavelet tensor, channels [Clo, 48) used) or Chi == 48 - Clo (only the remaining bands). */
+WDM_API int wdm_iwt4x4_cat(const float* lo, int Clo, const float* hi, int Chi, float* x, int n, int h, int w, int flags,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Conditional diffusion UNet engine.

@@ -46,3 +46,35 @@ def test_no_cpu_fallback():
         m(torch.zeros(1, 3, 8, 8))
     with pytest.raises(NotImplementedError):
         WaveletTransform(scale=1, dec=True)(torch.zeros(1, 3, 8, 8))
+
+
+def test_unet_config_validation_and_parameter_table_without_a_device():
+    """wdm_unet_param_count / _info only build the host-side model description: the 332 reference state-dict tensors
+    (+ temb.freqs) for raindrop_wavelet.yml, the same table for data.wavelet_in_unet (the frozen wavelet filters are not
+    engine parameters), and loud refusal of inconsistent configs."""
+    from wavedm_b200 import engine
+    from wavedm_b200.configs import default_config
+    lib = _lib.load()
+    cfg = default_config()
+    cs = engine.make_config_struct(cfg)
+    assert cs.in_channels == 96 and cs.out_ch == 3 and cs.wavelet_in_unet == 0
+    table = engine.param_table(cs)
+    assert len(table) == 333 and table[-1][0] == "temb.freqs" and table[0][0] == "temb.dense.0.weight"
+    assert sum(n for name, n in table if name != "temb.freqs") == 156492675
+    cfg.data.wavelet_in_unet = True
+    cfg.model.use_other_channels, cfg.model.in_channels, cfg.model.out_ch = False, 93, 48
+    cw = engine.make_config_struct(cfg)
+    assert cw.wavelet_in_unet == 1 and cw.in_channels == 96 and cw.out_ch == 48
+    tw = engine.param_table(cw)
+    assert [n for n, _ in tw] == [n for n, _ in table]
+    assert dict(tw)["conv_out.weight"] == 48 * 128 * 9
+    cw.out_ch = 3   # wavelet_in_unet needs 48 output channels
+    assert lib.wdm_unet_param_count(ctypes.byref(cw)) == _lib.WDM_ERR_BAD_ARG
+    cs.out_ch = 48  # and the plain mode at most 4
+    assert lib.wdm_unet_param_count(ctypes.byref(cs)) == _lib.WDM_ERR_BAD_ARG
+    # the fused restore() epilogue kernel validates shapes before touching the device
+    buf = (ctypes.c_float * 64)()
+    p16 = (ctypes.addressof(buf) + 15) & ~15
+    assert lib.wdm_iwt4x4_cat(p16, 3, p16, 44, p16, 1, 2, 2, 0, None) == _lib.WDM_ERR_BAD_SHAPE
+    assert lib.wdm_iwt4x4_cat(p16, 3, p16, 45, p16, 0, 2, 2, 0, None) == _lib.WDM_OK
+    assert lib.wdm_iwt4x4_nhwc(None, 48, 1, 2, p16, None) == _lib.WDM_ERR_BAD_ARG

@@ -111,3 +111,21 @@ def test_autograd_adjoint():
     gy = torch.randn(1, 48, 2, 2, device=_dev())
     (dec(x) * gy).sum().backward()
     assert (x.grad - iwt4x4(gy)).abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("full_hi", [False, True])
+def test_iwt_cat_equals_cat_then_iwt(full_hi):
+    """restore() epilogue kernel: IWT(cat([lo, hi bands])) (+clamp) without the concatenated tensor, bit-identical to the
+    two-step form and to the C oracle."""
+    from wavedm_b200.wavelet import iwt4x4_cat
+    g = torch.Generator().manual_seed(8)
+    lo = torch.randn(3, 3, 10, 14, generator=g)
+    full = torch.randn(3, 48, 10, 14, generator=g)
+    hi = full if full_hi else full[:, 3:].contiguous()
+    ref = DO.iwt(torch.cat([lo, full[:, 3:]], 1).numpy(), flags=1)
+    out = iwt4x4_cat(lo.to(DEV), hi.to(DEV), post_clamp=True)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    out2 = iwt4x4(torch.cat([lo, full[:, 3:]], 1).to(DEV), post_clamp=True)
+    assert torch.equal(out, out2)
+    with pytest.raises(ValueError):
+        iwt4x4_cat(lo.to(DEV), full[:, :10].contiguous().to(DEV))

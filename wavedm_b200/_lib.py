@@ -79,6 +79,7 @@ def load() -> ctypes.CDLL:
         "wdm_unet_profile_tc_bytes": (ctypes.c_double, [c_void_p]),
         "wdm_dwt4x4_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
         "wdm_iwt4x4_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+        "wdm_iwt4x4_cat": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
         "wdm_unet_param_count": (c_int, [c_void_p]),
         "wdm_unet_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, c_void_p]),
         "wdm_unet_packed_bytes": (c_size_t, [c_void_p, c_int]),

@@ -150,6 +150,45 @@ __global__ void __launch_bounds__(256) iwt4x4_direct_kernel(const float* __restr
     }
 }
 
+// ---- restore() epilogue (models/restoration.py:111-135): torch.cat([latent[:, :pred], hf[:, pred:]]) -> wavelet_rec ->
+// inverse_data_transform as ONE kernel: sub-band channel c comes from `lo` when c < Clo, else from `hi` (channel c of a
+// 48-channel tensor, or channel c - Clo of a tensor that holds only the remaining bands when hi_has_all == 0).
+template <bool kPost>
+__global__ void __launch_bounds__(256) iwt4x4_cat_kernel(const float* __restrict__ lo, int Clo, const float* __restrict__ hi,
+                                                         int Chi, int hi_off, float* __restrict__ x, long long nblocks,
+                                                         int h, int w) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nblocks) return;
+    const int j = (int)(idx % w);
+    const long long t1 = idx / w;
+    const int i = (int)(t1 % h);
+    const long long p = t1 / h;
+    const long long n = p / 3;
+    const int g = (int)(p - n * 3);
+    const long long plane = (long long)h * w;
+    const long long pix = (long long)i * w + j;
+    float in[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int c = 3 * k + g;
+        in[k] = c < Clo ? wdm_ldg_stream(lo + (n * Clo + c) * plane + pix)
+                        : wdm_ldg_stream(hi + (n * Chi + (c - hi_off)) * plane + pix);
+    }
+    float v[4][4];
+    wht16_inv(in, v);
+    const int W = 4 * w;
+    float* dst = x + ((p * (4LL * h) + 4 * i) * W + 4 * j);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float4 q;
+        if (kPost)
+            q = make_float4(post_clamp(v[r][0]), post_clamp(v[r][1]), post_clamp(v[r][2]), post_clamp(v[r][3]));
+        else
+            q = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+        wdm_stg_stream(reinterpret_cast<float4*>(dst + (long long)r * W), q);
+    }
+}
+
 // ---- wavelet_in_unet variants (models/unet.py:338-350, 393-394) -----------------------------------------------
 // DiffusionUNet(wavelet_in_unet=True) applies the DWT to each 3-channel half of its pixel-domain input INSIDE forward()
 // and the IWT to its 48-channel output, i.e. once per DDIM step. Here the forward transform is fused with the sampler's
@@ -568,4 +607,24 @@ extern "C" int wdm_gather_patches_dwt(const float* src0, const float* src1, int 
 
 extern "C" int wdm_iwt4x4_nhwc(const float* y, int ld, int P, int R, float* x, void* stream) {
     return wdm::launch_iwt_nhwc(y, ld, P, R, x, static_cast<cudaStream_t>(stream));
+}
+
+// lo: [n, Clo, h, w] supplies sub-band channels [0, Clo); hi: [n, Chi, h, w] supplies the rest -- Chi == 48 (a full
+// wavelet tensor, its first Clo channels are skipped) or Chi == 48 - Clo (only the remaining bands).
+extern "C" int wdm_iwt4x4_cat(const float* lo, int Clo, const float* hi, int Chi, float* x, int n, int h, int w, int flags,
+                              void* stream) {
+    if (!lo || !hi || !x) return WDM_ERR_BAD_ARG;
+    if (flags & ~WDM_IWT_POST_CLAMP) return WDM_ERR_BAD_ARG;
+    if (n < 0 || h <= 0 || w <= 0 || Clo < 1 || Clo > 47 || (Chi != 48 && Chi != 48 - Clo)) return WDM_ERR_BAD_SHAPE;
+    if (!wdm_aligned(x, 16)) return WDM_ERR_BAD_ALIGN;
+    if (n == 0) return WDM_OK;
+    const long long nblocks = (long long)n * 3 * h * w;
+    const unsigned grid = (unsigned)((nblocks + 255) / 256);
+    const int hi_off = Chi == 48 ? 0 : Clo;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (flags & WDM_IWT_POST_CLAMP)
+        iwt4x4_cat_kernel<true><<<grid, 256, 0, s>>>(lo, Clo, hi, Chi, hi_off, x, nblocks, h, w);
+    else
+        iwt4x4_cat_kernel<false><<<grid, 256, 0, s>>>(lo, Clo, hi, Chi, hi_off, x, nblocks, h, w);
+    return wdm_launch_status();
 }

@@ -16,7 +16,7 @@ import torch
 
 from . import logging as wlogging
 from . import metrics
-from .wavelet import dwt4x4, iwt4x4
+from .wavelet import dwt4x4, iwt4x4, iwt4x4_cat
 
 
 def data_transform(X):
@@ -69,7 +69,9 @@ class DiffusiveRestoration:
             wd_wav = dwt4x4(wd.contiguous(), pre_2xm1=True)
         if use_other and x_other is None:
             x_other = wd_wav[:, cfgm.other_channels_begin:].contiguous()
-        hf = wd_wav[:, cfgm.pred_channels:] if wd_wav is not None else x_other
+        # high-frequency bands for the final reconstruction: the full HFRM wavelet tensor (its channels >= pred_channels are
+        # used) or, with the HFRM bypassed, the caller's x_other (exactly the remaining bands)
+        hf = wd_wav if wd_wav is not None else x_other
         p_size = self.config.data.image_size
         h_list, w_list = self.overlapping_grid_indices(x_cond, output_size=p_size, r=r)
         corners = [(i, j) for i in h_list for j in w_list]
@@ -85,12 +87,14 @@ class DiffusiveRestoration:
         out: Dict[str, torch.Tensor] = {"latent": latent, "x_cond_wav": x_cond, "x_gt_wav": x_gt}
         lat = latent[:, :cfgm.pred_channels]
         if cfgm.pred_channels < cfgm.in_channels:
-            out["output"] = iwt4x4(torch.cat([lat, hf], dim=1), post_clamp=True)
+            # cat([low bands, high bands]) -> wavelet_rec -> inverse_data_transform as one kernel each (restoration.py:111-135)
+            lat = lat.contiguous()
+            out["output"] = iwt4x4_cat(lat, hf, post_clamp=True)
             if want_variants:
-                out["lrdiff_hrgt"] = iwt4x4(torch.cat([lat, x_gt[:, cfgm.pred_channels:]], dim=1), post_clamp=True)
-                out["lrgt_hrwdnet"] = iwt4x4(torch.cat([x_gt[:, :cfgm.pred_channels], hf], dim=1), post_clamp=True)
-                out["lrgt_hrcond"] = iwt4x4(torch.cat([x_gt[:, :cfgm.pred_channels], x_cond[:, cfgm.pred_channels:]], dim=1),
-                                            post_clamp=True)
+                gt_lo = x_gt[:, :cfgm.pred_channels].contiguous()
+                out["lrdiff_hrgt"] = iwt4x4_cat(lat, x_gt, post_clamp=True)
+                out["lrgt_hrwdnet"] = iwt4x4_cat(gt_lo, hf, post_clamp=True)
+                out["lrgt_hrcond"] = iwt4x4_cat(gt_lo, x_cond, post_clamp=True)
         else:
             out["output"] = iwt4x4(latent.contiguous(), post_clamp=True)
         if want_variants:

@@ -81,6 +81,27 @@ def iwt4x4(y: torch.Tensor, post_clamp: bool = False, impl: int = _lib.WDM_WT_IM
     return x
 
 
+def iwt4x4_cat(lo: torch.Tensor, hi: torch.Tensor, post_clamp: bool = False) -> torch.Tensor:
+    """IWT of ``torch.cat([lo, hi-bands], 1)`` without materialising the concatenation (models/restoration.py:111-135):
+    ``lo`` [N, Clo, h, w] supplies the first Clo sub-band channels; ``hi`` is either a full 48-channel wavelet tensor
+    (its channels [Clo, 48) are used) or holds exactly the remaining 48 - Clo bands."""
+    for t in (lo, hi):
+        if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 4:
+            raise TypeError("iwt4x4_cat expects CUDA float32 NCHW tensors (no CPU fallback)")
+    n, clo, h, w = lo.shape
+    if hi.shape[0] != n or hi.shape[2:] != (h, w) or hi.shape[1] not in (48, 48 - clo):
+        raise ValueError(f"incompatible shapes {tuple(lo.shape)} / {tuple(hi.shape)}")
+    lo, hi = lo.contiguous(), hi.contiguous()
+    x = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=lo.device)
+    if x.numel() == 0:
+        return x
+    with torch.cuda.device(lo.device):
+        st = _lib.load().wdm_iwt4x4_cat(lo.data_ptr(), clo, hi.data_ptr(), hi.shape[1], x.data_ptr(), n, h, w,
+                                        _lib.WDM_IWT_POST_CLAMP if post_clamp else 0, _lib.current_stream_ptr(lo.device))
+    _lib.check(st, "wdm_iwt4x4_cat")
+    return x
+
+
 class _DwtFn(torch.autograd.Function):
     """The packet basis is orthonormal, so the adjoint of the DWT is the IWT (and vice versa)."""
 
