@@ -118,6 +118,7 @@ def test_iwt_cat_equals_cat_then_iwt(full_hi):
     """restore() epilogue kernel: IWT(cat([lo, hi bands])) (+clamp) without the concatenated tensor, bit-identical to the
     two-step form and to the C oracle."""
     from wavedm_b200.wavelet import iwt4x4_cat
+    DEV = torch.device("cuda", 0)
     g = torch.Generator().manual_seed(8)
     lo = torch.randn(3, 3, 10, 14, generator=g)
     full = torch.randn(3, 48, 10, 14, generator=g)

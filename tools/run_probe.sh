@@ -1,9 +1,8 @@
 #!/bin/bash
-# GPU-box driver (run through gpurun)
+# GPU-box driver (run through gpurun): the round-end sequence the driver runs -> gpurun_out/
 cd $GRAFT_REPO_ROOT
 O=gpurun_out/probe.log
 : > $O
-for dbg in 0 8 6 7 5; do
-WDM_TC_DBG=$dbg timeout 100 python tools/tc_probe.py 2>&1 | grep "128->128.*full=1\|512->512.*taps=1 full=1" >> $O
-done
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) >> $O
+(timeout 120 python __graft_entry__.py smoke 2>&1 | tail -1) >> $O
 cat $O
