@@ -9,13 +9,15 @@
 // with the 128-byte swizzle, which is exactly the canonical K-major UMMA operand layout. B (packed weights
 // [Cout][taps*Cin], or a per-patch K matrix for attention) comes in through a 2-D / 3-D map the same way.
 //
-// One persistent CTA per SM, 8 warps, warp-specialised:
-//   warp 0     TMA producer          (STAGES-deep smem ring, full/empty mbarriers)
-//   warp 1     MMA issuer            (one elected lane; tcgen05.mma kind::f16 M=128 N=BN K=16, fp32 accum in TMEM)
-//   warp 2     TMEM allocator
-//   warps 4-7  epilogue              (tcgen05.ld 32 lanes x 32 columns -> bias/temb/residual -> bf16/fp32 global)
-// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the mainloop
-// of tile i+1.
+// One persistent CTA per SM, 12 warps, warp-specialised (see the role constants below):
+//   warps 0-7  epilogue              (tcgen05.ld 32 lanes x 32 columns -> bias/temb/residual/GroupNorm side-car -> a
+//                                     swizzled shared-memory chunk buffer -> TMA store; two warps per TMEM lane quarter)
+//   warp 8     TMA producer          (smem ring, full/empty mbarriers)
+//   warp 9     MMA issuer            (one elected lane; tcgen05.mma kind::f16 M=128 N=BN K=16, fp32 accum in TMEM)
+//   warp 10    TMEM allocator
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the mainloop of tile i+1.
+// Variants: CTA pairs (gemm_tc2_kernel, cta_group::2), halo macro-stages for the Cout = 128 3x3 convolutions
+// (Cfg<.., HALO>), swap-AB and pair<128,2> experiments (env-gated). Probes: WDM_TC_DBG, WDM_TC_TRACE (tools/tc_probe.py).
 #include <stdio.h>
 #include <stdlib.h>
 
