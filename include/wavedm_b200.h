@@ -204,6 +204,12 @@ typedef struct wdm_gemm_params {
     /* tensor-core path only: > 0 = store only the first `out_nchw_valid` (<= 32) output columns, as fp32 NCHW planes
      * out[(patch*valid + n)*Hout*Wout + pixel] (conv_out with Cout = 3 zero-padded to a 64-wide N tile). */
     int out_nchw_valid;
+    /* tensor-core path only. row_scale_out (with fuse_softmax): the probabilities are stored UNNORMALISED
+     * (exp(s - max), in (0, 1]) and 1 / sum of row m goes to row_scale_out[m] -- one pass over the scores instead of two,
+     * shared by both epilogue warp groups. row_scale: the epilogue multiplies accumulator row m by row_scale[m] before
+     * bias / residual (the P.V product that consumes those probabilities). */
+    float* row_scale_out;
+    const float* row_scale;
 } wdm_gemm_params;
 #define WDM_GEMM_IMPL_SIMT 0
 #define WDM_GEMM_IMPL_TC 1

@@ -31,7 +31,8 @@ class GemmParams(ctypes.Structure):
          ("temb_ld", ctypes.c_int), ("residual", ctypes.c_void_p), ("ldr", ctypes.c_int), ("out", ctypes.c_void_p)] + \
         [(n, ctypes.c_int) for n in ("ldo", "a_dtype", "b_dtype", "out_dtype")] + [("stats_out", ctypes.c_void_p), ("a_shared", ctypes.c_int), ("tail_1x1", ctypes.c_int),
                                                                                 ("src2", ctypes.c_void_p), ("C2", ctypes.c_int), ("ld2", ctypes.c_int),
-                                                                                ("fuse_softmax", ctypes.c_int), ("softmax_seg", ctypes.c_int), ("out_nchw_valid", ctypes.c_int)]
+                                                                                ("fuse_softmax", ctypes.c_int), ("softmax_seg", ctypes.c_int), ("out_nchw_valid", ctypes.c_int),
+                                                                                ("row_scale_out", ctypes.c_void_p), ("row_scale", ctypes.c_void_p)]
 
 
 def run_conv(x, x2, w, bias, stride, ups, temb, residual, dtype, impl, want_stats=False):
@@ -547,3 +548,52 @@ def test_unet_wavelet_in_unet_vs_reference_golden():
     with torch.no_grad():
         ref1 = O.unet_forward(sd, cfg, torch.from_numpy(g["x"]), torch.from_numpy(g["t"][:1]))
     assert (out1 - ref1).abs().max().item() <= 5e-5 * max(1.0, ref1.abs().max().item())
+
+
+@pytest.mark.parametrize("case", [(4, 256, 512, 0), (6, 64, 768, 64)])   # (patches, tokens L, C, softmax_seg): 16x16 and the 8x8 pair form
+@pytest.mark.parametrize("deferred", [False, True])
+def test_gemm_tc_fused_softmax_epilogue(case, deferred):
+    """Score GEMM with the row softmax in the epilogue (models/unet.py:176-182): normalised probabilities (single-group
+    form) or, with row_scale_out, unnormalised exp(s - max) + 1/sum per row (two-group form); both against torch."""
+    P, L, C, seg = case
+    G = 2 if seg else 1
+    Lg = G * L
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    q = (torch.randn(P * L, C, generator=g) * 0.7).bfloat16()
+    k = (torch.randn(P * L, C, generator=g) * 0.7).bfloat16()
+    scale = C ** -0.5
+    qd, kd = q.to(DEV), k.to(DEV)
+    out = torch.full((P * L, Lg), float("nan"), device=DEV, dtype=torch.bfloat16)
+    rs = torch.full((P * L,), float("nan"), device=DEV)
+    p = GemmParams()
+    p.src0, p.C0, p.ld0 = qd.data_ptr(), C, C
+    hw = int(round(L ** 0.5))
+    p.Hin = p.Hout = G * hw
+    p.Win = p.Wout = hw
+    p.taps, p.stride = 1, 1
+    p.B, p.ldb, p.b_batch_stride, p.b_layout = kd.data_ptr(), C, Lg * C, 0
+    p.M, p.N, p.K = P * L, Lg, C
+    p.alpha = scale
+    p.out, p.ldo = out.data_ptr(), Lg
+    p.a_dtype = p.b_dtype = p.out_dtype = 1
+    p.fuse_softmax, p.softmax_seg = 1, seg
+    if deferred:
+        p.row_scale_out = rs.data_ptr()
+    _lib.check(lib.wdm_gemm(ctypes.byref(p), _lib.WDM_GEMM_IMPL_TC, torch.cuda.current_stream().cuda_stream), "wdm_gemm")
+    torch.cuda.synchronize()
+    qf, kf = q.float().view(P, L, C), k.float().view(P, L, C)
+    s = torch.einsum("plc,pmc->plm", qf, kf) * scale                       # per patch [L, L]
+    ref = torch.softmax(s, dim=2)
+    got = out.float().cpu().view(P // G, G, L, G, L)
+    if deferred:
+        got = got * rs.cpu().view(P // G, G, L, 1, 1)
+        assert torch.isfinite(rs).all()
+    for a in range(G):
+        for b in range(G):
+            blk = got[:, a, :, b, :].reshape(P // G, L, L)
+            if a == b:
+                want = ref.view(P // G, G, L, L)[:, a]
+                assert (blk - want).abs().max().item() <= 6e-3, (a, b)
+            else:
+                assert not blk.any()   # block-diagonal: other patches of the group get probability zero

@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(256, 2) conv_small_cout_kernel(const T* __rest
 }  // namespace
 
 int launch_gemm_simt(const GemmParams& p, cudaStream_t s) {
+    if (p.row_scale || p.row_scale_out || p.fuse_softmax) return WDM_ERR_UNSUPPORTED;  // tensor-core epilogue features
     if (p.M <= 0 || p.N <= 0) return WDM_OK;
     if ((p.C0 % BK) || (p.C1 % BK) || (p.N % 8)) return WDM_ERR_BAD_SHAPE;
     if (p.tail_1x1) {

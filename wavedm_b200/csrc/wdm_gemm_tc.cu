@@ -71,6 +71,8 @@ struct TcArgs {
     int nchw_valid;            // > 0: fp32 NCHW output of the first nchw_valid columns only
     int dbg;                   // profiling probes (WDM_TC_DBG): 1 = no TMA loads, 2 = no MMAs (results are garbage)
     long long* trace;          // WDM_TC_TRACE: clock64 stamps of CTA 0's pipeline events (null = off)
+    float* row_scale_out;      // fused softmax: unnormalised probabilities + 1/sum per row (see epilogue_softmax2)
+    const float* row_scale;    // per-row factor applied to the accumulator (the P.V product after such a softmax)
     int epi_tma;               // bf16 results (and the residual) move through shared memory with TMA stores / loads
     int Wsrc;                  // subpix: source-grid width (epi_tma store box geometry)
 };
@@ -173,7 +175,12 @@ struct EpiSmem {
 
 template <int BN, int MT>
 __device__ __forceinline__ void epi_stage(const TcArgs& a, int mt0, int nt, int ew, int g, int lane, int row, const EpiSmem& es,
-                                          uint4 (&r0)[4], uint4 (&r1)[4]) {
+                                          uint4 (&r0)[4], uint4 (&r1)[4], float (&rsc)[MT]) {
+#pragma unroll
+    for (int hh = 0; hh < MT; ++hh) {
+        const long long m = (long long)(mt0 + hh) * kBM + row;
+        rsc[hh] = a.row_scale ? __ldg(a.row_scale + (m < a.M ? m : 0)) : 1.f;  // in flight while the mainloop still runs
+    }
     constexpr int kCh2 = (BN / 32 + 1) / 2, kF = MT * kCh2, kW = kCh2 * 32;  // this warp's chunks / columns per accumulator
     const int col0 = nt * BN + g * kW;
     if (a.bias || a.temb) {
@@ -207,7 +214,8 @@ __device__ __forceinline__ void epi_stage(const TcArgs& a, int mt0, int nt, int 
 // `tacc` = TMEM address of accumulator hh = 0, first column, this warp's lane quarter; accumulator hh is BN columns on.
 template <int BN, int MT>
 __device__ __forceinline__ void epi_rows(const TcArgs& a, const CUtensorMap* tmO, uint32_t tacc, int mt0, int nt, int ew, int g,
-                                         int lane, int row, const EpiSmem& es, uint4 (&r0)[4], uint4 (&r1)[4], bool tr = false) {
+                                         int lane, int row, const EpiSmem& es, uint4 (&r0)[4], uint4 (&r1)[4],
+                                         const float (&rsc)[MT], bool tr = false) {
     constexpr int kCh = BN / 32, kCh2 = (kCh + 1) / 2, kF = MT * kCh2, kW = kCh2 * 32;
     const float* sb = es.sb;
     const bool tma = a.epi_tma != 0;
@@ -241,6 +249,11 @@ __device__ __forceinline__ void epi_rows(const TcArgs& a, const CUtensorMap* tmO
             if (a.alpha != 1.f) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] *= a.alpha;
+            }
+            if (a.row_scale) {
+                const float rs = MT > 1 ? (hh ? rsc[MT - 1] : rsc[0]) : rsc[0];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= rs;
             }
             if (has_b) {
                 const float4* b4p = reinterpret_cast<const float4*>(sb + hh * kW + c * 32);
@@ -481,6 +494,79 @@ __device__ __forceinline__ void epilogue_softmax(const TcArgs& a, uint32_t tacc,
             }
         }
     }
+}
+
+// Attention-score epilogue, two warp groups (row_scale_out != null): group g owns columns [g*BN/2, (g+1)*BN/2) of the
+// key axis. Pass 1: row maximum of the half, exchanged with the partner warp (same TMEM lane quarter, other group)
+// through shared memory and a 64-thread named barrier. Pass 2: p = exp2(s*scale*log2e - max) ONCE per score, row sum,
+// bf16 p through the chunk buffer + TMA store. The probabilities stay unnormalised; 1 / (sum_0 + sum_1) goes to
+// row_scale_out[m] and the P.V contraction multiplies its accumulator rows by it. Against the single-group form: two
+// TMEM passes instead of three, one exponential per score instead of two, eight warps instead of four.
+template <int BN>
+__device__ __forceinline__ void epilogue_softmax2(const TcArgs& a, const CUtensorMap* tmO, uint32_t tacc, int mt, int ew, int g,
+                                                  int lane, int row, uint8_t* ebuf, float* xch) {
+    constexpr int kCh2 = BN / 64;
+    const long long m = (long long)mt * kBM + row;
+    const bool valid = m < a.M;
+    const int seg = a.softmax_seg;
+    const int c0 = seg > 0 ? (int)((m / seg) % (BN / seg)) * seg : 0, c1 = seg > 0 ? c0 + seg : BN;
+    const float sc = a.alpha * 1.4426950408889634f;
+    float* xmax = xch;            // [2][128]
+    float* xsum = xch + 2 * kBM;  // [2][128]
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < kCh2; ++c) {
+        const int ch = g * kCh2 + c;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tacc + ch * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = ch * 32 + j;
+            if (col >= c0 && col < c1) mx = fmaxf(mx, __uint_as_float(r[j]) * sc);
+        }
+    }
+    xmax[g * kBM + row] = mx;
+    ptx::named_bar_sync(1 + ew, 64);
+    mx = fmaxf(xmax[row], xmax[kBM + row]);
+    float sum = 0.f;
+    const int sw = (lane >> 1) & 3;
+    uint8_t* cb = ebuf + lane * 64;
+#pragma unroll 1
+    for (int c = 0; c < kCh2; ++c) {
+        const int ch = g * kCh2 + c;
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tacc + ch * 32, r);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = ch * 32 + j;
+            v[j] = (col >= c0 && col < c1) ? exp2f(fmaf(__uint_as_float(r[j]), sc, -mx)) : 0.f;
+            sum += v[j];
+        }
+        if (lane == 0) ptx::bulk_wait_group_read<0>();  // the previous chunk's TMA store has read the buffer
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(v[q * 8 + 2 * i], v[q * 8 + 2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(cb + ((q ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::tma_store_2d(tmO, ebuf, ch * 32, mt * kBM + ew * 32);
+            ptx::bulk_commit_group();
+        }
+    }
+    xsum[g * kBM + row] = sum;
+    ptx::named_bar_sync(1 + ew, 64);
+    if (g == 0 && valid) a.row_scale_out[m] = 1.0f / (xsum[row] + xsum[kBM + row]);
 }
 
 template <int BN, int MT, bool SWAP = false, bool HALO = false>
@@ -792,21 +878,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 }
             }
             uint4 r0[4], r1[4];
-            if (!a.softmax && !SWAP) epi_stage<BN, MT>(a, st * MT, nt, ew, g, lane, row, es, r0, r1);
+            float rsc[MT];
+            if (!a.softmax && !SWAP) epi_stage<BN, MT>(a, st * MT, nt, ew, g, lane, row, es, r0, r1, rsc);
             ptx::mbar_wait(&tfull[as], aph);
             ptx::tc_fence_after();
             if (threadIdx.x == 0 && tl < 2) tc_trace(a, 7 + 2 * tl);
             const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + as * (MT * BN);
             if (a.dbg == 5 || a.dbg == 9) {
+            } else if (a.softmax && a.row_scale_out) {
+#pragma unroll 1
+                for (int hh = 0; hh < MT; ++hh)
+                    epilogue_softmax2<BN>(a, &tmO, tacc + hh * BN, st * MT + hh, ew, g, lane, row, es.ebuf,
+                                          reinterpret_cast<float*>(tail + kTailBars));
             } else if (a.softmax) {
-                if (g == 0) {  // the row softmax needs the whole key axis in one thread
+                if (g == 0) {  // single-group form: the whole key axis in one thread
 #pragma unroll 1
                     for (int hh = 0; hh < MT; ++hh) epilogue_softmax<BN>(a, tacc + hh * BN, st * MT + hh, row);
                 }
             } else if (SWAP) {
                 epi_rows_swap(a, tacc, st * MT, nt, ew, g, lane);
             } else {
-                epi_rows<BN, MT>(a, &tmO, tacc, st * MT, nt, ew, g, lane, row, es, r0, r1,
+                epi_rows<BN, MT>(a, &tmO, tacc, st * MT, nt, ew, g, lane, row, es, r0, r1, rsc,
                                  a.trace && threadIdx.x == 0 && tl == 0);
             }
             if (threadIdx.x == 0 && tl < 2) tc_trace(a, 8 + 2 * tl);
@@ -1028,19 +1120,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 }
             }
             uint4 r0[4], r1[4];
-            if (!a.softmax) epi_stage<BN, MT>(a, mt, nt, ew, g, lane, row, es, r0, r1);
+            float rsc[MT];
+            if (!a.softmax) epi_stage<BN, MT>(a, mt, nt, ew, g, lane, row, es, r0, r1, rsc);
             ptx::mbar_wait(&tfull[as], aph);
             ptx::tc_fence_after();
             if (threadIdx.x == 0 && tl < 2) tc_trace(a, 7 + 2 * tl);
             const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + as * (MT * BN);
             if (a.dbg == 5 || a.dbg == 9) {
+            } else if (a.softmax && a.row_scale_out) {
+#pragma unroll 1
+                for (int hh = 0; hh < MT; ++hh)
+                    epilogue_softmax2<BN>(a, &tmO, tacc + hh * BN, mt + hh, ew, g, lane, row, es.ebuf,
+                                          reinterpret_cast<float*>(tail + kTailBars));
             } else if (a.softmax) {
                 if (g == 0) {
 #pragma unroll 1
                     for (int hh = 0; hh < MT; ++hh) epilogue_softmax<BN>(a, tacc + hh * BN, mt + hh, row);
                 }
             } else {
-                epi_rows<BN, MT>(a, &tmO, tacc, mt, nt, ew, g, lane, row, es, r0, r1,
+                epi_rows<BN, MT>(a, &tmO, tacc, mt, nt, ew, g, lane, row, es, r0, r1, rsc,
                                 a.trace && threadIdx.x == 0 && tl == 0);
             }
             if (threadIdx.x == 0 && tl < 2) tc_trace(a, 8 + 2 * tl);
@@ -1326,7 +1424,11 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         return e ? atoi(e) : 1;
     }();
     a.Wsrc = Wm;
-    a.epi_tma = epi_tma_enabled && p.out_dtype == DT_BF16 && !p.out_nchw_valid && !p.fuse_softmax && (BN % 64) == 0 &&
+    a.row_scale_out = p.fuse_softmax ? p.row_scale_out : nullptr;
+    a.row_scale = p.row_scale;
+    // (the two-group softmax epilogue always stores through TMA)
+    a.epi_tma = (epi_tma_enabled || a.row_scale_out) && p.out_dtype == DT_BF16 && !p.out_nchw_valid &&
+                (!p.fuse_softmax || p.row_scale_out) && (BN % 64) == 0 &&
                 (!subpix || (Wm <= 32 ? 32 % Wm == 0 : Wm % 32 == 0));
     CUtensorMap O = B;
     if (a.epi_tma) {

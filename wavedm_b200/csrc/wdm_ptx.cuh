@@ -275,6 +275,11 @@ __device__ __forceinline__ void ldg_64B(const uint4* p, uint4 (&r)[4]) {
                  : "l"(p + 2));
 }
 
+// named barrier among `nthreads` threads (ids 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t pred = 0;
     asm volatile(

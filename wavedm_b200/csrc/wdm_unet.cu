@@ -715,7 +715,12 @@ Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a, int G) {
     p.out = Pm, p.ldo = Lg, p.a_dtype = p.b_dtype = DT_BF16, p.out_dtype = DT_BF16;
     p.fuse_softmax = 1, p.softmax_seg = G > 1 ? L : 0;
     float* S = nullptr;
+    // deferred normalisation: the score epilogue stores exp(s - max) and 1/sum per row, the P.V epilogue applies it
+    float* rscale = nullptr;
     if (will_use_tc(c, p)) {
+        rscale = reinterpret_cast<float*>(c.ar->alloc((size_t)P * L * sizeof(float)));
+        if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
+        p.row_scale_out = rscale ? rscale : reinterpret_cast<float*>(16);
         run_gemm(c, p);
     } else {
         p.fuse_softmax = 0, p.softmax_seg = 0, p.out_dtype = DT_F32;
@@ -734,6 +739,7 @@ Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a, int G) {
     p.B = vT, p.b_batch_stride = (long long)C * Lg, p.ldb = Lg, p.b_layout = BL_NK;
     p.M = P * L, p.N = C, p.K = Lg, p.alpha = 1.f, p.bias = fused ? a.bo : a.qkv.pb + 2 * C;
     p.out = O.p, p.ldo = C, p.a_dtype = p.b_dtype = p.out_dtype = DT_BF16;
+    if (rscale) p.row_scale = rscale;
     if (fused) {
         p.residual = x.p, p.ldr = x.C;
         if ((p.M % 32) == 0 && (Hg * x.W) % 32 == 0) {
@@ -744,6 +750,7 @@ Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a, int G) {
     }
     run_gemm(c, p);
     if (S) c.ar->free(S);
+    if (rscale) c.ar->free(rscale);
     c.ar->free(Pm);
     c.ar->free(vT);
     if (fused) return O;
