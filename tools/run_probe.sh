@@ -3,6 +3,8 @@
 cd $GRAFT_REPO_ROOT
 O=gpurun_out/probe.log
 : > $O
-(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12) >> $O
-timeout 200 python tools/profile_unet.py --patches 64 --iters 10 --time --spans 2>&1 | grep -E "^P=| 16  12 | 16  24 |   8  12 |   8  24 " >> $O
+for v in 1 0; do
+WDM_TC_PAIR192=$v timeout 100 python tools/tc_probe.py 2>&1 | grep "768->768" >> $O
+WDM_TC_PAIR192=$v timeout 200 python tools/profile_unet.py --patches 64 --iters 10 --time 2>&1 | grep "^P=" >> $O
+done
 cat $O

@@ -1325,7 +1325,11 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     const bool use_pair = pair128x2 || (pair_enabled && (BN == 256 || (BN == 128 && pair128)) &&
                                         ((!p.b_batch_stride && !subpix) || tiles_per_batch_h % 2 == 0));
     bool pair192 = false;
-    if (use_pair && p.N % 192 == 0 && !p.fuse_softmax) {
+    static const int pair192_enabled = []() {
+        const char* e = getenv("WDM_TC_PAIR192");
+        return e ? atoi(e) : 1;
+    }();
+    if (use_pair && pair192_enabled && p.N % 192 == 0 && !p.fuse_softmax) {
         // 192-wide pair tiles when they fill the 74 CTA pairs better (e.g. N = 768 at 8x8: 64 tiles instead of 48)
         const long long mt2 = ((p.M + kBM - 1) / kBM + 1) / 2;
         const long long pairs = num_sms_tc() / 2;
