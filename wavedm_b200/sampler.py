@@ -51,15 +51,16 @@ class _StepGraph:
         def body():
             eng.gather(srcs, self.patches, out=self.xin)
             eng.forward_nhwc(self.xin, self.t, out=self.eps)
-        cur = torch.cuda.current_stream(dev)
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):   # warm-up outside capture: workspace allocation, function attributes, descriptors
-            body()
-        cur.wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            body()
+        with torch.cuda.device(dev):    # capture on the engine's device whatever the caller's current device is
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):   # warm-up outside capture: workspace allocation, function attributes, descriptors
+                body()
+            cur.wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                body()
 
     def load(self, x_cond, x, x_other, patches):
         self.x_cond.copy_(x_cond)
