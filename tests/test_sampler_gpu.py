@@ -310,3 +310,32 @@ def test_graph_replay_equals_eager_launches():
         xs_g, x0_g = DdimSampler(eng, use_graph=True).sample(*args)
         assert torch.equal(xs_e, xs_g) and torch.equal(x0_e, x0_g)
     assert len(eng._step_graphs) == 1
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+@pytest.mark.parametrize("chans", [(48, 3, 45), (3, 0, 0), (8, 5, 0)])
+def test_gather_patches_vs_torch(dtype, chans):
+    """wdm_gather_patches == crop + cat (models/ddm_wavelet.py:467-478) + NCHW->NHWC (+ bf16 rounding), pad channels zero,
+    odd channel totals included."""
+    from wavedm_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(13)
+    B, h, w, R = 2, 40, 56, 16
+    Cpad = 128 if dtype else 96
+    srcs = [torch.randn(B, c, h, w, generator=g) for c in chans if c]
+    pats = torch.tensor([[0, 0, 0], [1, 24, 40], [0, 7, 13], [1, 16, 3], [0, 24, 40]], dtype=torch.int32)
+    td = torch.bfloat16 if dtype else torch.float32
+    out = torch.full((len(pats), R, R, Cpad), 5.0, dtype=td, device=DEV)
+    sd = [s.to(DEV) for s in srcs] + [None] * (3 - len(srcs))
+    ptr = lambda t: t.data_ptr() if t is not None else 0
+    st = lib.wdm_gather_patches(ptr(sd[0]), chans[0], ptr(sd[1]), chans[1], ptr(sd[2]), chans[2], B, h, w,
+                                pats.to(DEV).data_ptr(), len(pats), R, Cpad, out.data_ptr(), dtype,
+                                torch.cuda.current_stream().cuda_stream)
+    _lib.check(st, "wdm_gather_patches")
+    torch.cuda.synchronize()
+    ctot = sum(chans)
+    for q, (n, hi, wi) in enumerate(pats.tolist()):
+        ref = torch.cat([s[n, :, hi:hi + R, wi:wi + R] for s in srcs], 0).permute(1, 2, 0)   # [R, R, ctot]
+        got = out[q].float().cpu()
+        assert torch.equal(got[..., :ctot], ref.to(td).float())
+        assert not got[..., ctot:].any()

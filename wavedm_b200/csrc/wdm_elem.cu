@@ -381,40 +381,49 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ i
 }
 
 // ---------------------------------------------------------------------------------------------- gather
-// grid (R rows, P patches); smem tile [Cpad][R+1]
+// grid (R rows, P patches). The row of R pixels x Cpad channels is staged in OUTPUT layout ([x][Cpad], output dtype) in
+// 32-bit words with an odd row pitch: the scatter of one channel over consecutive x and the row-contiguous copy-out (16-byte
+// global stores) are both bank-conflict free. (The first version staged fp32 [c][x] and wrote 2-byte global stores:
+// 116 us per 64-patch step = 22 % of the HBM roofline.)
 template <typename TO>
 __global__ void __launch_bounds__(256) gather_patches_kernel(const GatherParams p) {
-    extern __shared__ float tile[];
+    extern __shared__ __align__(16) unsigned char smem_g[];
+    constexpr int kPerWord = 4 / (int)sizeof(TO);
+    uint32_t* tile = reinterpret_cast<uint32_t*>(smem_g);
     const int y = blockIdx.x, pi = blockIdx.y;
-    const int R = p.R, Cpad = p.Cpad, pitch = R + 1;
+    const int R = p.R, Cpad = p.Cpad;
+    const int wpr = Cpad / kPerWord, pitch = wpr | 1;
     const int img = p.patches[pi * 3], hi = p.patches[pi * 3 + 1], wi = p.patches[pi * 3 + 2];
     const int c01 = p.Cs[0] + p.Cs[1];
     const int ctot = c01 + (p.nsrc > 2 ? p.Cs[2] : 0);
-    for (int i = threadIdx.x; i < Cpad * R; i += blockDim.x) {
+    for (int i = threadIdx.x; i < ctot * R; i += blockDim.x) {
         const int c = i / R, x = i - c * R;
-        float v = 0.f;
-        if (c < ctot) {
-            const float* s;
-            int cs, Cs;
-            if (c < p.Cs[0])
-                s = p.src[0], cs = c, Cs = p.Cs[0];
-            else if (c < c01)
-                s = p.src[1], cs = c - p.Cs[0], Cs = p.Cs[1];
-            else
-                s = p.src[2], cs = c - c01, Cs = p.Cs[2];
-            v = __ldg(s + (((long long)img * Cs + cs) * p.h + (hi + y)) * p.w + (wi + x));
-        }
-        tile[c * pitch + x] = v;
+        const float* s;
+        int cs, Cs;
+        if (c < p.Cs[0])
+            s = p.src[0], cs = c, Cs = p.Cs[0];
+        else if (c < c01)
+            s = p.src[1], cs = c - p.Cs[0], Cs = p.Cs[1];
+        else
+            s = p.src[2], cs = c - c01, Cs = p.Cs[2];
+        const float v = __ldg(s + (((long long)img * Cs + cs) * p.h + (hi + y)) * p.w + (wi + x));
+        reinterpret_cast<TO*>(tile + x * pitch)[c] = TO(v);
     }
     __syncthreads();
-    TO* o = reinterpret_cast<TO*>(p.out) + ((long long)pi * R + y) * R * Cpad;
-    for (int j = threadIdx.x; j < R * Cpad; j += blockDim.x) {
-        const int x = j / Cpad, c = j - x * Cpad;
-        const float v = tile[c * pitch + x];
-        if (sizeof(TO) == 4)
-            reinterpret_cast<float*>(o)[j] = v;
-        else
-            reinterpret_cast<__nv_bfloat16*>(o)[j] = __float2bfloat16(v);
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<TO*>(p.out) + ((long long)pi * R + y) * R * Cpad);
+    const int valid_words = (ctot + kPerWord - 1) / kPerWord;  // channels >= ctot are zero padding
+    const bool odd_tail = kPerWord == 2 && (ctot & 1);          // last valid word holds one real channel
+    const int qpr = wpr >> 2;
+    for (int e = threadIdx.x; e < R * qpr; e += blockDim.x) {
+        const int x = e / qpr, cw = (e - x * qpr) * 4;
+        const uint32_t* t = tile + x * pitch + cw;
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            w[k] = cw + k < valid_words ? t[k] : 0u;
+            if (odd_tail && cw + k == valid_words - 1) w[k] &= 0x0000ffffu;
+        }
+        dst[e] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -662,7 +671,9 @@ int launch_temb(const TembParams& p, cudaStream_t s) {
 int launch_gather_patches(const GatherParams& p, cudaStream_t s) {
     if (p.P <= 0) return WDM_OK;
     if (p.nsrc < 1 || p.nsrc > 3) return WDM_ERR_BAD_ARG;
-    const size_t smem = (size_t)p.Cpad * (p.R + 1) * sizeof(float);
+    if (p.Cpad % (p.out_dtype == DT_F32 ? 4 : 8)) return WDM_ERR_BAD_SHAPE;  // 16-byte copy-out units
+    const size_t wpr = p.out_dtype == DT_F32 ? (size_t)p.Cpad : (size_t)p.Cpad / 2;
+    const size_t smem = (size_t)p.R * (wpr | 1) * 4;
     if (smem > 96 * 1024) return WDM_ERR_BAD_SHAPE;
     dim3 grid(p.R, p.P);
     if (p.out_dtype == DT_F32) {
