@@ -396,8 +396,7 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(const GatherParams 
     const int img = p.patches[pi * 3], hi = p.patches[pi * 3 + 1], wi = p.patches[pi * 3 + 2];
     const int c01 = p.Cs[0] + p.Cs[1];
     const int ctot = c01 + (p.nsrc > 2 ? p.Cs[2] : 0);
-    for (int i = threadIdx.x; i < ctot * R; i += blockDim.x) {
-        const int c = i / R, x = i - c * R;
+    auto src_of = [&](int c, int x) -> const float* {
         const float* s;
         int cs, Cs;
         if (c < p.Cs[0])
@@ -406,8 +405,32 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(const GatherParams 
             s = p.src[1], cs = c - p.Cs[0], Cs = p.Cs[1];
         else
             s = p.src[2], cs = c - c01, Cs = p.Cs[2];
-        const float v = __ldg(s + (((long long)img * Cs + cs) * p.h + (hi + y)) * p.w + (wi + x));
-        reinterpret_cast<TO*>(tile + x * pitch)[c] = TO(v);
+        return s + (((long long)img * Cs + cs) * p.h + (hi + y)) * p.w + (wi + x);
+    };
+    // thread = (x, channel lane): no per-element division when R divides the block (R = 16, 64, 256 in practice); kU
+    // independent loads in flight per thread before the first shared-memory store
+    constexpr int kU = 8;
+    if ((blockDim.x % R) == 0) {
+        const int x = threadIdx.x % R, cl = threadIdx.x / R, cstep = blockDim.x / R;
+        TO* col = reinterpret_cast<TO*>(tile + x * pitch);
+        for (int c0 = cl; c0 < ctot; c0 += kU * cstep) {
+            float v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int c = c0 + u * cstep;
+                v[u] = c < ctot ? __ldg(src_of(c, x)) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int c = c0 + u * cstep;
+                if (c < ctot) col[c] = TO(v[u]);
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < ctot * R; i += blockDim.x) {
+            const int c = i / R, x = i - c * R;
+            reinterpret_cast<TO*>(tile + x * pitch)[c] = TO(__ldg(src_of(c, x)));
+        }
     }
     __syncthreads();
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<TO*>(p.out) + ((long long)pi * R + y) * R * Cpad);
