@@ -145,6 +145,8 @@ TC_CASES = [
     (3, 192, 0, 768, 8, 3, 1, 0, 0, False),     # odd patch count: M = 192 -> partial last tile (8x8)
     (2, 1536, 0, 768, 8, 3, 1, 0, 1, True),     # deepest level shape, K = 13824
     (1, 128, 0, 128, 32, 1, 1, 0, 0, False),    # 1x1, 32-wide rows
+    (5, 128, 0, 256, 4, 1, 1, 0, 0, True),      # M = 80: rows 64..79 valid in one warp only (M % 32 != 0), residual
+    (3, 128, 0, 128, 4, 3, 1, 0, 1, False),     # M = 48, 4x4 patches (8 per tile), 3x3
 ]
 
 

@@ -1,4 +1,9 @@
 #!/bin/bash
+# GPU-box driver (run through gpurun): the round-end sequence the driver runs -> gpurun_out/
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/run_probe.sh'
 cd $GRAFT_REPO_ROOT
-timeout 300 compute-sanitizer --tool racecheck python -m pytest tests/test_unet_gpu.py -m gpu -x -q -k "fused_softmax or groupnorm_sidecar" > gpurun_out/racecheck.log 2>&1
-grep -c "" gpurun_out/racecheck.log
+O=gpurun_out/probe.log
+: > $O
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) >> $O
+(timeout 120 python __graft_entry__.py smoke 2>&1 | tail -1) >> $O
+cat $O

@@ -239,6 +239,12 @@ __device__ __forceinline__ void epi_rows(const TcArgs& a, const CUtensorMap* tmO
         }
         ptx::tmem_ld_32x32b_x32(tacc + hh * BN + ch * 32, r);
         ptx::tmem_ld_wait();
+        if (tma) {
+            // the TMA store of the previous chunk must have read the chunk buffer (lane 0 committed it); warp-uniform, i.e.
+            // outside the per-row `valid` branch (M need not be a multiple of 32)
+            if (lane == 0 && a.dbg != 8) ptx::bulk_wait_group_read<0>();
+            __syncwarp();
+        }
         if (tr && f < 4) tc_trace(a, 16 + 2 * f);
         const long long m = e.m;
         if (e.valid) {
@@ -299,11 +305,6 @@ __device__ __forceinline__ void epi_rows(const TcArgs& a, const CUtensorMap* tmO
                     }
                 }
                 uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + e.orow * a.ldo + n);
-                if (tma) {
-                    // the TMA store of the previous chunk must have read the buffer (lane 0 committed it)
-                    if (lane == 0 && a.dbg != 8) ptx::bulk_wait_group_read<0>();
-                    __syncwarp();
-                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t w[4];
