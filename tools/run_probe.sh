@@ -4,6 +4,7 @@
 cd $GRAFT_REPO_ROOT
 O=gpurun_out/probe.log
 : > $O
-(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) >> $O
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4) >> $O
 (timeout 120 python __graft_entry__.py smoke 2>&1 | tail -1) >> $O
+timeout 200 python tools/profile_unet.py --patches 64 --iters 10 --time 2>&1 | grep "^P=" >> $O
 cat $O

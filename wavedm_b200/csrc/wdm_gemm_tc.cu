@@ -938,7 +938,7 @@ struct Cfg2 {
     static constexpr int kSmem = kStages * kStage + 1024 + kTail;
 };
 
-template <int BN, int MT = 1>
+template <int BN, int MT = 1, int GRP = 2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -1055,11 +1055,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 ptx::mbar_wait(&tempty[as], aph ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * (MT * BN);
+                // GRP k-blocks per issue group. Traced (clock64 stamps around the group, since removed from this loop because
+                // they slow the issuing thread): ~88 cycles per tcgen05.mma issue plus ~490 cycles of barrier waits / fence /
+                // commits per group = 1197 cycles per 8 MMAs against 1024 cycles of tensor work at N = 256 (86 %). GRP = 3
+                // amortises that overhead but leaves only two coarse groups in the 6-stage ring and measured slower end to
+                // end (WDM_TC_GROUP=3: 5.29 vs 5.11 ms per UNet call), so 2 stays the default
                 for (int kb = 0; kb < kblocks;) {
-                    const int nb = (kblocks - kb) >= 2 ? 2 : 1;  // two k-blocks per issue group (see the 1-CTA kernel)
-                    uint32_t sidx[2];
+                    const int nb = (kblocks - kb) >= GRP ? GRP : (kblocks - kb);
+                    uint32_t sidx[GRP];
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
+                    for (int j = 0; j < GRP; ++j) {
                         if (j < nb) {
                             sidx[j] = (it + j) % C::kStages;
                             ptx::mbar_wait(&full[sidx[j]], ((it + j) / C::kStages) & 1);
@@ -1069,7 +1074,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     if (lane == 0) {
                         if (it == 0) tc_trace(a, 4);
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
+                        for (int j = 0; j < GRP; ++j) {
                             if (j < nb && a.dbg != 2) {
                                 const uint32_t sa = ptx::smem_u32(smem + sidx[j] * C::kStage);
                                 const uint64_t db = make_smem_desc(sa + MT * kABytes);
@@ -1083,7 +1088,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < 2; ++j)
+                        for (int j = 0; j < GRP; ++j)
                             if (j < nb) ptx::umma2_commit_mc(&empty[sidx[j]], 3);
                         if (kb + nb == kblocks) {
                             ptx::umma2_commit_mc(&tfull[as], 3);
@@ -1209,16 +1214,16 @@ int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& A
     return wdm_launch_status();
 }
 
-template <int BN, int MT = 1>
+template <int BN, int MT = 1, int GRP = 2>
 int launch_pair(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& A2, const CUtensorMap& B, const CUtensorMap& O,
                 const TcArgs& a, cudaStream_t s) {
     using C = Cfg2<BN, MT>;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, MT, GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     const int tiles = ((a.m_tiles + 2 * MT - 1) / (2 * MT)) * a.n_tiles;
     const int pairs = num_sms_tc() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    e = wdm_launch_pdl(gemm_tc2_kernel<BN, MT>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, A2, B, O, a);
+    e = wdm_launch_pdl(gemm_tc2_kernel<BN, MT, GRP>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, A2, B, O, a);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     return wdm_launch_status();
 }
@@ -1497,6 +1502,12 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     }
     if (use_pair) {
         if (BN == 128) return pair128x2 ? launch_pair<128, 2>(A0, A1, A2, B, O, a, s) : launch_pair<128>(A0, A1, A2, B, O, a, s);
+        static const int grp = []() {
+            const char* e = getenv("WDM_TC_GROUP");
+            return e ? atoi(e) : 2;  // 3 measured: UNet call 5.29 vs 5.11 ms (fewer, coarser groups in a 6-stage ring)
+        }();
+        if (grp == 3)
+            return pair192 ? launch_pair<192, 1, 3>(A0, A1, A2, B, O, a, s) : launch_pair<256, 1, 3>(A0, A1, A2, B, O, a, s);
         return pair192 ? launch_pair<192>(A0, A1, A2, B, O, a, s) : launch_pair<256>(A0, A1, A2, B, O, a, s);
     }
     const bool allow2 = !a.b_batched || (a.tiles_per_batch % 2 == 0);
