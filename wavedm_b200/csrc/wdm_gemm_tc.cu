@@ -938,7 +938,7 @@ struct Cfg2 {
     static constexpr int kSmem = kStages * kStage + 1024 + kTail;
 };
 
-template <int BN, int MT = 1, int GRP = 2>
+template <int BN, int MT = 1, int GRP = 2, bool PB = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -998,8 +998,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
     if (warp == kWarpTma) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
-        uint32_t it = 0;
-        for (int tile = cluster_id; tile < num_tiles; tile += nclusters) {
+        uint32_t it = 0, tlp = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += nclusters, ++tlp) {
             const int st = tile / a.n_tiles, nt = tile - st * a.n_tiles;
             int n_img[MT], cy0[MT];  // this CTA's m-tiles: (st * 2 + rank) * MT + h
 #pragma unroll
@@ -1012,6 +1012,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const int bb = a.b_batched ? (st * 2 * MT) / a.tiles_per_batch : 0;
             const int nrow = nt * BN + (int)rank * (BN / 2);
             int kb_lin = 0;
+            const uint32_t gq0 = tlp * (uint32_t)((kblocks + 1) / 2);  // PB: groups issued before this tile
             for (int g = 0; g < a.nseg; ++g) {
                 const CUtensorMap* tm = g == 0 ? &tmA0 : (g == 1 ? &tmA1 : &tmA2);
                 const int staps = a.seg_taps[g], skc = a.seg_kc[g];
@@ -1021,22 +1022,39 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     if (a.subpix) dy = (bb >> 1) - 1 + (tap >> 1), dx = (bb & 1) - 1 + (tap & 1);  // bb = output phase
                     const int cx = dx - pad;
                     for (int kc = 0; kc < skc; ++kc, ++it, ++kb_lin) {
-                        const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
-                        ptx::mbar_wait(&empty[s], ph ^ 1);
+                        // PB: ONE full / empty barrier per pair of k-blocks (the issue group): slot = group counter % (stages / 2),
+                        // the pair's k-blocks use stages 2*slot and 2*slot + 1; groups never straddle tiles
+                        uint32_t s, ph;
+                        uint64_t* fbar;
+                        bool first = true;
+                        int nb_grp = 1;
+                        if (PB) {
+                            constexpr uint32_t np = C::kStages / 2;
+                            const uint32_t gq = gq0 + (uint32_t)(kb_lin >> 1), slot = gq % np;
+                            s = 2 * slot + (kb_lin & 1), ph = (gq / np) & 1;
+                            fbar = &full[slot];
+                            first = (kb_lin & 1) == 0;
+                            nb_grp = (kblocks - (kb_lin & ~1)) >= 2 ? 2 : 1;
+                            if (first) ptx::mbar_wait(&empty[slot], ph ^ 1);
+                        } else {
+                            s = it % C::kStages, ph = (it / C::kStages) & 1;
+                            fbar = &full[s];
+                            ptx::mbar_wait(&empty[s], ph ^ 1);
+                        }
                         if (lane == 0) {
                             uint8_t* sa = smem + s * C::kStage;
                             uint8_t* sb = sa + MT * kABytes;
                             if (a.dbg == 1 || a.dbg == 9) {
-                                if (leader) ptx::mbar_arrive(&full[s]);
+                                if (leader && first) ptx::mbar_arrive(fbar);
                             } else {
-                            if (leader) ptx::mbar_arrive_expect_tx(&full[s], 2 * C::kStage);  // bytes of BOTH CTAs
+                            if (leader && first) ptx::mbar_arrive_expect_tx(fbar, nb_grp * 2 * C::kStage);  // bytes of BOTH CTAs
 #pragma unroll
                             for (int h = 0; h < MT; ++h)
-                                ptx::tma2_load_4d(sa + h * kABytes, tm, &full[s], kc * kBK, cx, cy0[h] + dy - pad, n_img[h]);
+                                ptx::tma2_load_4d(sa + h * kABytes, tm, fbar, kc * kBK, cx, cy0[h] + dy - pad, n_img[h]);
                             if (a.b_batched)
-                                ptx::tma2_load_3d(sb, &tmB, &full[s], kb_lin * kBK, nrow, bb);
+                                ptx::tma2_load_3d(sb, &tmB, fbar, kb_lin * kBK, nrow, bb);
                             else
-                                ptx::tma2_load_2d(sb, &tmB, &full[s], kb_lin * kBK, nrow);
+                                ptx::tma2_load_2d(sb, &tmB, fbar, kb_lin * kBK, nrow);
                             }
                             if (it == 0) tc_trace(a, 3);
                         }
@@ -1063,12 +1081,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 for (int kb = 0; kb < kblocks;) {
                     const int nb = (kblocks - kb) >= GRP ? GRP : (kblocks - kb);
                     uint32_t sidx[GRP];
+                    uint32_t pslot = 0;
+                    if (PB) {
+                        static_assert(!PB || GRP == 2, "paired barriers: two k-blocks per group");
+                        constexpr uint32_t np = C::kStages / 2;
+                        const uint32_t gq = tl * (uint32_t)((kblocks + 1) / 2) + (uint32_t)(kb >> 1);
+                        pslot = gq % np;
+                        sidx[0] = 2 * pslot, sidx[GRP - 1] = 2 * pslot + 1;
+                        ptx::mbar_wait(&full[pslot], (gq / np) & 1);
+                    } else {
 #pragma unroll
                     for (int j = 0; j < GRP; ++j) {
                         if (j < nb) {
                             sidx[j] = (it + j) % C::kStages;
                             ptx::mbar_wait(&full[sidx[j]], ((it + j) / C::kStages) & 1);
                         }
+                    }
                     }
                     ptx::tc_fence_after();
                     if (lane == 0) {
@@ -1087,9 +1115,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                                 }
                             }
                         }
+                        if (PB) {
+                            ptx::umma2_commit_mc(&empty[pslot], 3);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < GRP; ++j)
-                            if (j < nb) ptx::umma2_commit_mc(&empty[sidx[j]], 3);
+                            for (int j = 0; j < GRP; ++j)
+                                if (j < nb) ptx::umma2_commit_mc(&empty[sidx[j]], 3);
+                        }
                         if (kb + nb == kblocks) {
                             ptx::umma2_commit_mc(&tfull[as], 3);
                             if (tl < 2) tc_trace(a, 5 + tl);
@@ -1214,16 +1246,16 @@ int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& A
     return wdm_launch_status();
 }
 
-template <int BN, int MT = 1, int GRP = 2>
+template <int BN, int MT = 1, int GRP = 2, bool PB = false>
 int launch_pair(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& A2, const CUtensorMap& B, const CUtensorMap& O,
                 const TcArgs& a, cudaStream_t s) {
     using C = Cfg2<BN, MT>;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, MT, GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, MT, GRP, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     const int tiles = ((a.m_tiles + 2 * MT - 1) / (2 * MT)) * a.n_tiles;
     const int pairs = num_sms_tc() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    e = wdm_launch_pdl(gemm_tc2_kernel<BN, MT, GRP>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, A2, B, O, a);
+    e = wdm_launch_pdl(gemm_tc2_kernel<BN, MT, GRP, PB>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, A2, B, O, a);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     return wdm_launch_status();
 }
@@ -1508,6 +1540,12 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         }();
         if (grp == 3)
             return pair192 ? launch_pair<192, 1, 3>(A0, A1, A2, B, O, a, s) : launch_pair<256, 1, 3>(A0, A1, A2, B, O, a, s);
+        static const int pairbar = []() {
+            const char* e = getenv("WDM_TC_PAIRBAR");
+            return e ? atoi(e) : 1;  // measured: UNet call 5.15 -> 4.82 ms (the issuing thread was the bottleneck)
+        }();
+        if (pairbar)  // one full / empty barrier per two-k-block issue group
+            return pair192 ? launch_pair<192, 1, 2, true>(A0, A1, A2, B, O, a, s) : launch_pair<256, 1, 2, true>(A0, A1, A2, B, O, a, s);
         return pair192 ? launch_pair<192>(A0, A1, A2, B, O, a, s) : launch_pair<256>(A0, A1, A2, B, O, a, s);
     }
     const bool allow2 = !a.b_batched || (a.tiles_per_batch % 2 == 0);
