@@ -171,7 +171,7 @@ def run_reference_arm(args):
         return
     import torch
     threads = os.cpu_count() or 1
-    per_step_target = 8.0
+    per_step_target = float(os.environ.get("WDM_BENCH_REF_STEP_SECONDS", "8.0"))  # CPU seconds of work per timed step
     cpu_restore_sample(1, 2, threads)  # build weights, warm caches
     probe = cpu_restore_sample(1, 2, threads) / 2
     n = int(max(2, min(DDIM_STEPS, per_step_target / max(probe, 1e-3))))
