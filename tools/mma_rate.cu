@@ -123,7 +123,58 @@ void run2(int grid) {
     cudaFree(d);
 }
 
+// Cost of the pieces of the issue-group protocol for ONE thread (the MMA issuer): try_wait on an already-complete
+// mbarrier, tcgen05.fence::after_thread_sync, tcgen05.commit (no MMAs pending), and a wait+fence+commit round.
+__global__ void __launch_bounds__(128, 1) k3(int iters, long long* out) {
+    __shared__ uint64_t ready, sink[8];
+    __shared__ uint32_t slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) { ptx::tmem_alloc(&slot, 64); ptx::tmem_relinquish(); }
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(&ready, 1);
+        for (int i = 0; i < 8; ++i) ptx::mbar_init(&sink[i], 1);
+        ptx::fence_mbar_init();
+        ptx::mbar_arrive(&ready);
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 1 && lane == 0) {
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) ptx::mbar_wait(&ready, 0);
+        long long t1 = clock64();
+        for (int i = 0; i < iters; ++i) ptx::tc_fence_after();
+        long long t2 = clock64();
+        for (int i = 0; i < iters; ++i) ptx::umma_commit(&sink[i & 7]);
+        long long t3 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            ptx::mbar_wait(&ready, 0);
+            ptx::mbar_wait(&ready, 0);
+            ptx::tc_fence_after();
+            ptx::umma_commit(&sink[i & 7]);
+            ptx::umma_commit(&sink[(i + 1) & 7]);
+        }
+        long long t4 = clock64();
+        if (blockIdx.x == 0) out[0] = t1 - t0, out[1] = t2 - t1, out[2] = t3 - t2, out[3] = t4 - t3;
+    }
+    __syncthreads();
+    if (warp == 0) ptx::tmem_dealloc(slot, 64);
+}
+
+void run3() {
+    long long* d; cudaMalloc(&d, 32);
+    const int iters = 2000;
+    k3<<<148, 128>>>(iters, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[4] = {0, 0, 0, 0}; cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
+    printf("issuer protocol pieces (cycles each, one thread): try_wait(complete) %.1f, fence::after_thread_sync %.1f, "
+           "tcgen05.commit %.1f, [2 waits + fence + 2 commits] %.1f  err=%s\n", h[0] / (double)iters, h[1] / (double)iters,
+           h[2] / (double)iters, h[3] / (double)iters, cudaGetErrorString(e));
+    cudaFree(d);
+}
+
 int main() {
+    run3();
     run2<256, 4>(148); run2<256, 8>(148); run2<256, 16>(148);
     run2<128, 4>(148); run2<128, 8>(148); run2<128, 16>(148);
     run<256>("cg1", 1); run<256>("cg1", 148);
