@@ -32,9 +32,11 @@ def make_patch_table(n_images: int, corners: Sequence[Tuple[int, int]], device) 
 
 
 class _StepGraph:
-    """One captured CUDA graph of (patch gather -> UNet forward) over persistent buffers: a P <= 16 UNet call is
-    ~190 dependent launches of a few microseconds each, i.e. bound by the host's launch rate (2.7 ms per call at P = 1);
-    replaying the captured sequence removes the host from the loop. Cached on the engine per problem shape."""
+    """One captured CUDA graph of (patch gather -> UNet forward) over persistent buffers: a P <= 16 UNet call is ~180
+    dependent launches of a few microseconds each; replaying the captured sequence takes the host (ctypes calls,
+    tensor-map encoding) out of the loop. Measured gain 3 % (2.43 -> 2.35 ms per step at P = 1): the small-batch call is
+    bound by the serial depth of the K loops, not by the launch rate. Cached on the engine per problem
+    shape; bit-identical to eager launches."""
 
     def __init__(self, eng, x_cond, x, x_other, patches):
         dev = eng.device
