@@ -10,6 +10,7 @@ Generates the committed golden vectors under tests/golden/ by importing the UNMO
   * models/ddm_wavelet.py:437-506   generalized_steps_overlapping            -> ddim_small.npz
   * models/ddm_wavelet.py:87-105    get_beta_schedule                        -> ddim_small.npz['betas']
   * models/unet.py:203-206,338-350  DiffusionUNet(wavelet_in_unet=True) + the pixel-domain sampler -> unet_wiu.npz
+  * models/arch.py:132-253          HFRM (plain-PyTorch mirror in wavedm_b200/hfrm.py)                 -> hfrm.npz
   * models/restoration.py:63-168    the DWT -> sample -> x0_preds[-5] -> IWT -> clamp sandwich (config #1,
                                     with HFRM bypassed: x_other = HF bands of the DWT of the synthetic
                                     gt)                                      -> sandwich_full.npz
@@ -101,12 +102,42 @@ def golden_wavelet_in_unet(ref_unet, ref_ddm):
     print("unet_wiu.npz ok; keys", len(sd_ref), "corners", len(corners), "steps", len(x0p))
 
 
+def fill_params_deterministically(module, seed):
+    """The same pseudo-random parameter values for any module with the same state-dict key order and shapes (the
+    default init leaves HFRM's beta / gamma at zero, which would hide most of the network from the comparison)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for _, v in module.state_dict().items():
+            v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+
+
+def golden_hfrm():
+    """models/arch.py:132-253 (HFRM, the one-shot high-frequency refinement CNN) -> hfrm.npz: state-dict
+    layout + the output of the reference module on a seeded input with deterministically filled parameters."""
+    import models.arch as ref_arch
+    kw = dict(in_channel=3, dim=32, mid_blk_num=6, enc_blk_nums=[2, 2, 2, 4], dec_blk_nums=[2, 2, 2, 2])  # ddm_wavelet.py:137
+    net = ref_arch.HFRM(**kw).eval()
+    fill_params_deterministically(net, 71)
+    x = torch.rand(2, 3, 32, 48, generator=torch.Generator().manual_seed(72))
+    with torch.no_grad():
+        y = net(x)
+    keys = list(net.state_dict().keys())
+    shapes = [list(v.shape) for v in net.state_dict().values()]
+    np.savez(os.path.join(OUT, "hfrm.npz"), x=x.numpy(), y=y.numpy(), keys=np.array(keys), nparams=sum(int(np.prod(s_)) for s_ in shapes),
+             shapes=np.array([",".join(map(str, s_)) for s_ in shapes]), param_seed=71)
+    print("hfrm.npz ok;", len(keys), "tensors", sum(int(np.prod(s_)) for s_ in shapes), "parameters; out range",
+          float(y.min()), float(y.max()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref_unet, ref_wavelet, ref_ddm, ref_sampling, ref_metrics = import_reference()
     if "--only-wiu" in sys.argv:   # regenerate just the wavelet_in_unet vectors
         golden_wavelet_in_unet(ref_unet, ref_ddm)
+        return
+    if "--only-hfrm" in sys.argv:
+        golden_hfrm()
         return
 
     # ---------------------------------------------------------------- DWT / IWT
@@ -247,6 +278,7 @@ def main():
 
     print("sandwich_full.npz ok; psnr", float(psnr), "latent range", float(lat.min()), float(lat.max()))
     golden_wavelet_in_unet(ref_unet, ref_ddm)
+    golden_hfrm()
 
 
 if __name__ == "__main__":

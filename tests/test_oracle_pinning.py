@@ -159,3 +159,24 @@ def test_oracle_state_dict_is_bit_identical_to_reference_init():
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code, repo], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_hfrm_mirror_vs_reference_golden():
+    """wavedm_b200/hfrm.py (the plain-PyTorch mirror of models/arch.py:132-253 that the constructor strict-loads and
+    restore() calls once per image): same state-dict keys / shapes as the reference module and the same
+    output on a seeded input with deterministically filled parameters."""
+    from wavedm_b200.hfrm import HFRM
+    g = golden("hfrm.npz")
+    net = HFRM(in_channel=3, dim=32, mid_blk_num=6, enc_blk_nums=[2, 2, 2, 4], dec_blk_nums=[2, 2, 2, 2]).eval()
+    sd = net.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    assert [",".join(map(str, v.shape)) for v in sd.values()] == [str(s) for s in g["shapes"]]
+    assert sum(v.numel() for v in sd.values()) == int(g["nparams"])
+    gen = torch.Generator().manual_seed(int(g["param_seed"]))
+    with torch.no_grad():
+        for v in sd.values():
+            v.copy_(torch.randn(v.shape, generator=gen) * 0.1)
+        y = net(torch.from_numpy(g["x"]))
+    ref = torch.from_numpy(g["y"])
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max() <= 1e-4 * ref.abs().max()
