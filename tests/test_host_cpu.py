@@ -139,3 +139,53 @@ def test_two_rank_gloo_weight_broadcast_and_gather(tmp_path):
     import torch.multiprocessing as mp
     port = 29500 + (os.getpid() % 400)
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/datasets"), reason="reference checkout not present")
+def test_raindrop_dataset_matches_reference_loader(tmp_path):
+    """Only in the build container: the host-side loader mirror (wavedm_b200/raindrop_data.py) yields exactly what the
+    reference's datasets/raindrop.py yields on the same files -- the batch-tuple contract the hot path consumes
+    (x[6,H,W] in [0,1] = input || gt, image id, total), whole-image mode (resize to 720x480, multiples of 16) and
+    patch mode (same random crops under the same seed)."""
+    import subprocess
+    import sys
+    import numpy as np
+    import PIL.Image
+    root = os.path.join(str(tmp_path), "raindrop_test")
+    os.makedirs(os.path.join(root, "input"))
+    os.makedirs(os.path.join(root, "gt"))
+    rng = np.random.default_rng(3)
+    for name, (h, w) in (("7_rain.png", (300, 460)), ("12_rain.png", (480, 720))):
+        for sub, nm in (("input", name), ("gt", name.replace("rain", "clean"))):
+            PIL.Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(os.path.join(root, sub, nm))
+    code = (
+        "import sys, os, random, types, torch, torchvision\n"
+        "root, which, repo, out = sys.argv[1:5]\n"
+        "if which == 'ref':\n"
+        "    for n in ('skimage','skimage.color'): sys.modules.setdefault(n, types.ModuleType(n))\n"
+        "    sys.path.insert(0, '/root/reference'); os.chdir('/root/reference')\n"
+        "    from datasets.raindrop import RainDropDataset\n"
+        "else:\n"
+        "    sys.path.insert(0, repo)\n"
+        "    from wavedm_b200.raindrop_data import RainDropDataset\n"
+        "tf = torchvision.transforms.Compose([torchvision.transforms.ToTensor()])\n"
+        "res = {}\n"
+        "for mode in (False, True):\n"
+        "    random.seed(5)\n"
+        "    ds = RainDropDataset(root, patch_size=64, n=3, transforms=tf, filelist=None, parse_patches=mode)\n"
+        "    random.seed(6)\n"
+        "    for i in range(len(ds)):\n"
+        "        x, img_id, total = ds[i]\n"
+        "        res[f'{mode}_{i}'] = (x, img_id, total)\n"
+        "torch.save(res, out)\n")
+    outs = {}
+    for which in ("ref", "ours"):
+        out = os.path.join(str(tmp_path), which + ".pt")
+        r = subprocess.run([sys.executable, "-c", code, root, which, REPO, out], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[which] = torch.load(out)
+    assert outs["ref"].keys() == outs["ours"].keys() and len(outs["ref"]) == 4
+    for k, (x, img_id, total) in outs["ref"].items():
+        xo, ido, to = outs["ours"][k]
+        assert img_id == ido and x.shape == xo.shape and torch.equal(x, xo) and torch.equal(total, to), k
+    assert outs["ours"]["False_0"][0].shape[1] % 16 == 0 and outs["ours"]["True_0"][0].shape == (3, 6, 64, 64)
