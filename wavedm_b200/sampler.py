@@ -78,10 +78,15 @@ class DdimSampler:
     #: captured graphs (with their persistent buffers) kept per engine, least recently used evicted
     GRAPH_CACHE_ENTRIES = 4
 
-    def __init__(self, engine: UNetEngine, max_patches: Optional[int] = None, use_graph: Optional[bool] = None):
+    def __init__(self, engine: UNetEngine, max_patches: Optional[int] = None, use_graph: Optional[bool] = None,
+                 mirror_rng: bool = True):
         self.engine = engine
         self.max_patches = int(max_patches or engine.max_patches)
         self.use_graph = use_graph
+        #: the reference evaluates ``c1 * torch.randn_like(x)`` with c1 = 0 at every step (ddm_wavelet.py:502): the value
+        #: is irrelevant but the device's default generator advances, which decides the initial noise of the NEXT image
+        #: (restoration.py:177). Drawing the same throw-away tensor keeps seeded multi-image runs in step with it.
+        self.mirror_rng = mirror_rng
 
     @torch.no_grad()
     def sample(self, x: torch.Tensor, x_cond: torch.Tensor, x_other: Optional[torch.Tensor], seq: Sequence[int],
@@ -133,6 +138,8 @@ class DdimSampler:
                 eng.forward_nhwc(xin[:n], t, out=eps[p0:p0 + n])
             slot = k if keep_history else 0
             eng.ddim_step(eps, patches, first, xt, x0_hist[slot], xs_hist[slot], at, at_next)
+            if self.mirror_rng:
+                torch.randn_like(xt)
             xt = xs_hist[slot]
         return xs_hist, x0_hist
 
@@ -154,6 +161,8 @@ class DdimSampler:
             slot = k if keep_history else 0
             eng.ddim_step(sg.eps, sg.patches, first, sg.xt, x0_hist[slot], xs_hist[slot], float(alphas[i_t + 1]),
                           float(alphas[j_t + 1]))
+            if self.mirror_rng:
+                torch.randn_like(sg.xt)
             sg.xt.copy_(xs_hist[slot])
         return xs_hist, x0_hist
 
