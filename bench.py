@@ -18,6 +18,16 @@ broadcast and the gather of restored images to rank 0 (inside the timed region).
   roofline_dwt : the DWT kernel's HBM GB/s on >L2 working sets (the metric's second half)
   cpu_baseline : the CPU oracle port of the same path timed on this box's host cores (bounded sample)
 
+  parity       : (N = 1) the north_star's own parity config -- BASELINE.json configs[1]: batch 16, 256x256, 50 DDIM steps --
+                 run on the fp32 engine AND on the benched bf16 engine against the golden vectors the reference itself
+                 produced (tests/golden/sandwich_s50.npz): achieved latent / image / PSNR errors in the line
+  gpu_eager_baseline : (N = 1) the reference's PyTorch path (oracle port, eager + cuDNN) on THIS B200, fp32 and bf16
+                 autocast, bounded sample -- the honest GPU comparator; a reported baseline, not the product
+
+  --config 5   : BASELINE.json configs[4] (512x512, grid_r = 16 -> 25 overlapping patches per image, 100 DDIM steps,
+                 32 images per GPU); lines kept under profiles/
+  --precision fp32 : the parity-mode engine (3xTF32 tensor-core contractions / FFMA)
+
 The HFRM (one-shot high-frequency CNN, SURVEY.md 8f-1 "next") is bypassed in BOTH arms: the 45 high-frequency
 channels fed to the UNet are the HF bands of the DWT of the synthetic ground truth (the reference's own
 `if 0:` branch, restoration.py:99-100), so the two arms time the same computation.
@@ -34,9 +44,10 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 UNET_GFLOP_PER_PATCH = 79.945  # algorithmic 2*MAC per 96x64x64 patch per UNet call
-H = W = 256
-DDIM_STEPS = 50
+H = W = 256          # overwritten by --config 5 (512)
+DDIM_STEPS = 50      # the schedule the metric is quoted on; --config 5 uses 100
 SEED = 61
+GRID_R = 16
 
 
 def parse():
@@ -45,16 +56,32 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 5],
+                    help="BASELINE.json configs index + 0: 2 = batch 64/GPU, 256x256, 50 DDIM steps (the metric's config); "
+                         "5 = configs[4]: 512x512, 25 patches/image (grid_r 16), 100 DDIM steps, 32 images/GPU")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default 64; 32 for --config 5)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--ddim-steps", type=int, default=DDIM_STEPS)
-    ap.add_argument("--max-patches", type=int, default=64)
+    ap.add_argument("--ddim-steps", type=int, default=None)
+    ap.add_argument("--max-patches", type=int, default=None, help="patches per UNet call (default 64; 160 for --config 5)")
     ap.add_argument("--wavelet-in-unet", action="store_true",
                     help="NOT the BASELINE config: data.wavelet_in_unet (DWT / IWT inside the network at every DDIM step, "
                          "pixel-domain sampler, out_ch 48); the line is labelled accordingly")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
-    return ap.parse_args()
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (N = 1 only anyway)")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the PyTorch-eager GPU comparator (N = 1 only anyway)")
+    args = ap.parse_args()
+    global H, W, DDIM_STEPS
+    if args.config == 5:
+        H = W = 512
+        DDIM_STEPS = 100
+    if args.batch is None:
+        args.batch = 32 if args.config == 5 else 64
+    if args.ddim_steps is None:
+        args.ddim_steps = DDIM_STEPS
+    if args.max_patches is None:
+        args.max_patches = 160 if args.config == 5 else 64   # 800 patches per DDIM step = 5 calls of 160
+    return args
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -125,7 +152,8 @@ def make_cfg(precision, device, wavelet_in_unet=False):
 # ------------------------------------------------------------------------------------------------ CPU oracle arm
 def cpu_restore_sample(n_images, ddim_steps, threads):
     """The CPU oracle port (oracle/unet_oracle.py + oracle/dwt_oracle.c) of the same path on `n_images` images
-    for `ddim_steps` DDIM steps of the 50-step schedule. Returns seconds."""
+    for `ddim_steps` DDIM steps of the DDIM_STEPS-step schedule (overlapping 64x64 patches on the grid_r grid when the
+    wavelet-domain image is larger than one patch). Returns seconds."""
     import torch
     from oracle import dwt_oracle as DO
     from oracle import unet_oracle as O
@@ -143,13 +171,19 @@ def cpu_restore_sample(n_images, ddim_steps, threads):
         x_cond = torch.from_numpy(DO.dwt(x[:, :3].numpy(), flags=1))
         x_gt = torch.from_numpy(DO.dwt(x[:, 3:].numpy(), flags=1))
         x_other = x_gt[:, 3:]
+        hl, wl = O.overlapping_grid_indices(H // 4, W // 4, 64, GRID_R)
         xs, x0p = O.ddim_sample_overlapping(lambda a, tt: O.unet_forward(sd, cfg, a, tt), noise, x_cond, x_other,
-                                            seq_run, betas, [(0, 0)], 64)
+                                            seq_run, betas, [(i, j) for i in hl for j in wl], 64)
         lat = x0p[-5] if len(x0p) >= 5 else x0p[-1]
         out = DO.iwt(torch.cat([lat[:, :3], x_other], 1).numpy(), flags=1)
     dt = time.perf_counter() - t0
     assert out.shape == (n_images, 3, H, W)
     return dt
+
+
+def patches_per_image():
+    n = lambda d: len(range(0, d // 4 - 64 + 1, GRID_R)) + (1 if (d // 4 - 64) % GRID_R else 0)
+    return n(H) * n(W)
 
 
 def cpu_baseline(target_seconds, threads):
@@ -161,7 +195,7 @@ def cpu_baseline(target_seconds, threads):
     t = cpu_restore_sample(1, steps, threads)
     ips = (steps / DDIM_STEPS) / t  # images/s normalised to the 50-step schedule
     return {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": f"1 image 256x256, {steps} of {DDIM_STEPS} DDIM steps (UNet 1 patch/step) + DWT/IWT in {t:.2f} s, "
+            "sample": f"1 image {H}x{W}, {steps} of {DDIM_STEPS} DDIM steps (UNet {patches_per_image()} patch(es)/step) + DWT/IWT in {t:.2f} s, "
                       f"scaled to {DDIM_STEPS} steps; torch {threads} threads (oracle/unet_oracle.py + dwt_oracle.c)"}
 
 
@@ -180,9 +214,9 @@ def run_reference_arm(args):
     ts = [cpu_restore_sample(1, n, threads) for _ in range(args.steps)]
     t = sum(ts) / len(ts)
     val = (n / DDIM_STEPS) / t
-    sample = (f"each step = 1 image 256x256, {n} of {DDIM_STEPS} DDIM steps + DWT/IWT, scaled to {DDIM_STEPS} steps; "
+    sample = (f"each step = 1 image {H}x{W}, {n} of {DDIM_STEPS} DDIM steps + DWT/IWT, scaled to {DDIM_STEPS} steps; "
               f"CPU oracle port, torch {threads} threads")
-    line = {"impl": "reference", "metric": "restored images/sec @256x256, 50-step DDIM", "value": val, "unit": "images/s",
+    line = {"impl": "reference", "metric": metric_name(), "value": val, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, torch.__version__),
@@ -190,6 +224,10 @@ def run_reference_arm(args):
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def metric_name():
+    return f"restored images/sec @{H}x{W}, {DDIM_STEPS}-step DDIM"
 
 
 def workload_config(args, torch_version):
@@ -200,18 +238,179 @@ def workload_config(args, torch_version):
                 "global_batch": args.batch * args.gpus, "images_per_gpu": args.batch, "ddim_steps": args.ddim_steps,
                 "l2": "inputs+activations per step far exceed L2 (126 MB); weights 313 MB bf16", "torch": torch_version,
                 "hfrm": "not part of this mode (x_other = None, restoration.py:98-104)"}
-    return {"workload": f"BASELINE.json configs[2]: batch {args.batch}/GPU, 256x256, {args.ddim_steps} DDIM steps, "
-                        f"{args.precision} UNet (1 64x64 wavelet patch/image), raindrop_wavelet.yml, seed-61 default-init weights",
+    which = "configs[4] (512x512 patched sampling, grid_r 16)" if args.config == 5 else "configs[2]"
+    return {"workload": f"BASELINE.json {which}: batch {args.batch}/GPU, {H}x{W}, {args.ddim_steps} DDIM steps, "
+                        f"{args.precision} UNet ({patches_per_image()} 64x64 wavelet patch(es)/image), raindrop_wavelet.yml, "
+                        f"seed-61 default-init weights",
             "global_batch": args.batch * args.gpus, "images_per_gpu": args.batch, "ddim_steps": args.ddim_steps,
             "l2": "inputs+activations per step far exceed L2 (126 MB); weights 313 MB bf16", "torch": torch_version,
             "hfrm": "bypassed in both arms (x_other = HF bands of DWT(gt))"}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def parity_block(dev, precisions=("fp32", "bf16"), batch=16, slots=(3, 12)):
+    """The north_star's own parity config (BASELINE.json configs[1]: batch 16, 256x256, 50 DDIM steps, fp32; gates
+    |PSNR_new - PSNR_ref| < 0.01 dB and per-pixel |d| < 1e-3 on the element restore() returns, restoration.py:106-135)
+    through the public API, against tests/golden/sandwich_s50.npz -- two independent B = 1 runs of the UNMODIFIED reference
+    (oracle/make_golden.py --only-s50; the reference sampler is batch-1 only), placed at two slots of a 16-image batch whose
+    other images are random. Returns the ACHIEVED errors per engine precision (tests/test_parity_s50_gpu.py asserts on the
+    same numbers). No oracle code runs here: the checker is the committed golden file."""
+    import numpy as np
+    import torch
+    from wavedm_b200.harness import build_restorer
+    from wavedm_b200.metrics import torchPSNR
+    g = np.load(os.path.join(REPO, "tests", "golden", "sandwich_s50.npz"))
+    seeds = [int(v) for v in g["seeds"]]
+    gen = torch.Generator().manual_seed(1234)
+    x = torch.rand(batch, 6, 256, 256, generator=gen)
+    noise = torch.randn(batch, 3, 64, 64, generator=gen)
+    for slot, seed in zip(slots, seeds):
+        gs = torch.Generator().manual_seed(seed)
+        x[slot] = torch.rand(1, 6, 256, 256, generator=gs)[0]
+        noise[slot] = torch.randn(1, 3, 64, 64, generator=gs)[0]
+    lat_ref = torch.from_numpy(g["latent_m5"])
+    out_ref = torch.from_numpy(g["out"])
+    res = {"config": f"BASELINE.json configs[1]: batch {batch}, 256x256, {int(g['steps'])} DDIM steps; golden = the reference's own "
+                     f"classes on CPU fp32 (tests/golden/sandwich_s50.npz, images at batch slots {list(slots)})",
+           "gates": {"image_max_abs": 1e-3, "psnr_db": 0.01}}
+    for prec in precisions:
+        cfg = make_cfg(prec, dev)
+        restorer = build_restorer(cfg, dev, sampling_timesteps=int(g["steps"]), max_patches=64, seed=SEED)
+        xd = x.to(dev)
+        x_other = restorer.diffusion.wavelet_dec(2 * xd[:, 3:].contiguous() - 1.0)[:, 3:].contiguous()
+        t0 = time.perf_counter()
+        r = restorer.restore_batch(xd, r=GRID_R, noise=noise.to(dev), x_other=x_other)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        lat = r["latent"].cpu()[list(slots)]
+        out = r["output"].cpu()[list(slots)]
+        dps = [abs(float(torchPSNR(x[s_:s_ + 1, 3:], out[i:i + 1])) - float(g["psnr"][i])) for i, s_ in enumerate(slots)]
+        unsat = (out_ref > 0) & (out_ref < 1)
+        tc_n, simt_n = restorer.diffusion.model.module.engine().counters()
+        res[prec] = {"latent_max_abs": float((lat - lat_ref).abs().max()),
+                     "latent_max_rel": float((lat - lat_ref).abs().max() / lat_ref.abs().max()),
+                     "latent_rel_l2": float((lat - lat_ref).norm() / lat_ref.norm()),
+                     "image_max_abs": float((out - out_ref).abs().max()),
+                     "image_mean_abs": float((out - out_ref).abs().mean()),
+                     "image_max_abs_unsaturated_px": float((out - out_ref).abs()[unsat].max()) if unsat.any() else 0.0,
+                     "unsaturated_px_frac": float(unsat.float().mean()),
+                     "psnr_abs_diff_db": max(dps), "psnr_ref_db": [float(v) for v in g["psnr"]],
+                     "tc_launches": tc_n, "simt_launches": simt_n, "seconds": dt}
+        res[prec]["pass"] = bool(res[prec]["image_max_abs"] < 1e-3 and res[prec]["psnr_abs_diff_db"] < 0.01)
+        del restorer
+        torch.cuda.empty_cache()
+    return res
+
+
+def gpu_eager_baseline(dev, batch, ddim_sample_steps=3):
+    """The reference's own PyTorch path on THIS GPU (SURVEY.md 8d / BASELINE.md 4: "the honest GPU comparator"): the oracle
+    port of models/unet.py + the DDIM loop (bit-equal to the reference modules on CPU, oracle/make_golden.py) run with CUDA
+    tensors -- PyTorch eager + cuDNN/cuBLAS. A reported baseline like cpu_baseline: bounded sample (`ddim_sample_steps` of
+    the 50-step schedule, scaled), three variants: fp32 with torch's default TF32-conv setting, strict fp32 (TF32 off), and
+    bf16 autocast; batched the way OUR sampler batches (all images' patches in one UNet call -- kinder to eager than the
+    reference's batch-1 loop), plus the reference's real batch-1 semantics for one image."""
+    import torch
+    from oracle import unet_oracle as O
+    cfg = O.default_config()
+    sd = {k: v.to(dev) for k, v in O.init_state_dict(cfg, seed=SEED).items()}
+    betas = O.beta_schedule(cfg).to(dev)
+    seq = O.sampling_seq(1000, 50)
+    seq_run = seq[len(seq) - ddim_sample_steps:]
+    out = {"what": "oracle port of the reference's PyTorch modules on cuda (eager + cuDNN), same sampler shape as the bench "
+                   f"step ({batch} images x 1 patch per UNet call); {ddim_sample_steps} of 50 DDIM steps timed after one warm-up "
+                   "pass, scaled to 50", "unit": "images/s", "torch": torch.__version__}
+
+    def run(n_img, mode):
+        g = torch.Generator().manual_seed(SEED)
+        xc = torch.randn(n_img, 48, 64, 64, generator=g).to(dev)
+        xo = torch.randn(n_img, 45, 64, 64, generator=g).to(dev)
+        xn = torch.randn(n_img, 3, 64, 64, generator=g).to(dev)
+
+        def model(a, tt):
+            if mode == "bf16_autocast":
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return O.unet_forward(sd, cfg, a, tt).float()
+            return O.unet_forward(sd, cfg, a, tt)
+        tf32 = mode != "fp32_strict"
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = False if mode == "fp32_strict" else old[1]
+        try:
+            with torch.no_grad():
+                # the oracle's sampler is per image (reference semantics); batch it over images like our sampler does
+                def once():
+                    xt = xn
+                    for i_t in reversed(seq_run):
+                        t = torch.full((1,), float(i_t), device=dev)   # one timestep for all patches (ddm_wavelet.py:457)
+                        et = model(torch.cat([xc, xt, xo], 1), t)
+                        at = O.compute_alpha(betas, torch.full((1,), i_t, device=dev, dtype=torch.long))
+                        at_next = O.compute_alpha(betas, torch.full((1,), max(i_t - 20, -1), device=dev, dtype=torch.long))
+                        x0 = (xt - et * (1 - at).sqrt()) / at.sqrt()
+                        xt = at_next.sqrt() * x0 + (1 - at_next).sqrt() * et
+                    return xt
+                once()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+                e0.record()
+                once()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / 1e3
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+    for mode in ("fp32_tf32conv_default", "fp32_strict", "bf16_autocast"):
+        try:
+            t = run(batch, mode)
+            out[mode] = {"value": batch * (ddim_sample_steps / 50.0) / t, "ms_per_unet_call": t / ddim_sample_steps * 1e3,
+                         "images_per_call": batch}
+        except Exception as e:  # an OOM of the eager path must not take the bench line down
+            out[mode] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+    try:
+        t1 = run(1, "fp32_tf32conv_default")
+        out["batch1_fp32_tf32conv_default"] = {"value": (ddim_sample_steps / 50.0) / t1, "ms_per_unet_call": t1 / ddim_sample_steps * 1e3,
+                                               "note": "the reference's real operating point: one image per UNet call (ddm_wavelet.py:486)"}
+    except Exception as e:
+        out["batch1_fp32_tf32conv_default"] = {"error": repr(e)[:200]}
+    del sd
+    torch.cuda.empty_cache()
+    return out
+
+
+def dram_traffic_per_launch():
+    """roofline.traffic: dram__bytes_read + write per contraction launch from the committed ncu capture of ONE UNet call,
+    valid only for the library build it was taken on (the capture records the sha256 of libwavedm_b200.so)."""
+    import hashlib
+    try:
+        with open(os.path.join(REPO, "wavedm_b200", "libwavedm_b200.so"), "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()[:16]
+    except Exception:
+        sha = None
+    best = None
+    pdir = os.path.join(REPO, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if name.endswith("_traffic.json"):
+            try:
+                with open(os.path.join(pdir, name)) as f:
+                    d = json.load(f)
+            except Exception:
+                continue
+            d["file"] = "profiles/" + name
+            if d.get("lib_sha16") == sha:
+                return d["traffic_bytes_per_launch"], {"file": d["file"], "lib_sha16": sha, "same_build": True}
+            best = d
+    if best is not None:
+        return None, {"file": best["file"], "lib_sha16": best.get("lib_sha16"), "same_build": False,
+                      "stale_value": best.get("traffic_bytes_per_launch"), "this_lib_sha16": sha}
+    return None, {"this_lib_sha16": sha}
+
+
 def dwt_roofline(dev, peak):
     import torch
     from wavedm_b200 import _lib
     lib = _lib.load()
+    H = W = 256  # the DWT half of the metric is quoted at 256x256 whatever --config says
     B = 256
     nbuf = 3
     xs = [torch.randn(B, 3, H, W, device=dev) for _ in range(nbuf)]
@@ -282,19 +481,19 @@ def main():
 
     def step_device():
         if args.wavelet_in_unet:
-            return restorer.restore_batch(x_dev, r=16, noise=noise_dev)["output"]
+            return restorer.restore_batch(x_dev, r=GRID_R, noise=noise_dev)["output"]
         xo = restorer.diffusion.wavelet_dec(2 * x_dev[:, 3:].contiguous() - 1.0)[:, 3:].contiguous()
-        res = restorer.restore_batch(x_dev, r=16, noise=noise_dev, x_other=xo)
+        res = restorer.restore_batch(x_dev, r=GRID_R, noise=noise_dev, x_other=xo)
         return res["output"]
 
-    gathered = None
-    if world > 1:
-        gathered = [torch.empty(B, 3, H, W, device=dev) for _ in range(world)] if rank == 0 else None
+    # the final gather of restored images: one all-gather into a preallocated [world*B, 3, H, W] tensor --
+    # every rank receives in parallel over NVSwitch (a gather to rank 0 serialises 7 receives on one GPU)
+    gathered = torch.empty(world * B, 3, H, W, device=dev) if world > 1 else None
 
     def step_full():
         out = step_device()
         if world > 1:
-            dist.gather(out, gathered, dst=0)
+            dist.all_gather_into_tensor(gathered, out.contiguous())
         return out
 
     out_pin = torch.empty(B, 3, H, W).pin_memory()
@@ -303,12 +502,12 @@ def main():
         xh = x_pin.to(dev, non_blocking=True)
         nh = noise_pin.to(dev, non_blocking=True)
         if args.wavelet_in_unet:
-            out = restorer.restore_batch(xh, r=16, noise=nh)["output"]
+            out = restorer.restore_batch(xh, r=GRID_R, noise=nh)["output"]
         else:
             xo = restorer.diffusion.wavelet_dec(2 * xh[:, 3:].contiguous() - 1.0)[:, 3:].contiguous()
-            out = restorer.restore_batch(xh, r=16, noise=nh, x_other=xo)["output"]
+            out = restorer.restore_batch(xh, r=GRID_R, noise=nh, x_other=xo)["output"]
         if world > 1:
-            dist.gather(out, gathered, dst=0)
+            dist.all_gather_into_tensor(gathered, out.contiguous())
         out_pin.copy_(out, non_blocking=True)  # pinned destination; the timed region ends with a device synchronize
         return out_pin
 
@@ -362,18 +561,13 @@ def main():
     # achieved = ALGORITHMIC flops of the contraction work (79.945 GFLOP per 64x64 patch and UNet call, the
     # reference's own operation count) / CUDA-event time of exactly those launches; the executed count is lower (sub-pixel
     # upsample-conv -6.0, four-contraction attention -1.5 GFLOP per patch and call) and is reported next to it
-    n_patch_calls = B * args.ddim_steps
+    n_patch_calls = B * patches_per_image() * args.ddim_steps
     alg_fl = UNET_GFLOP_PER_PATCH * 1e9 * n_patch_calls
     ach_tf = alg_fl / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
     exe_tf = k_fl / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
-    traffic = None
-    try:
-        with open(os.path.join(REPO, "profiles", "r01_traffic.json")) as f:
-            traffic = json.load(f)["traffic_bytes_per_launch"]  # dram read+write per launch from the committed ncu capture
-    except Exception:
-        pass
+    traffic, traffic_src = dram_traffic_per_launch()
     roof = {"kernel": kname, "bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": ach_tf / peak_tf, "traffic": traffic,
+            "frac": ach_tf / peak_tf, "traffic": traffic, "traffic_src": traffic_src,
             "executed_tflops": exe_tf, "executed_frac": exe_tf / peak_tf,
             "algorithmic_flops_per_launch": alg_fl / max(k_n, 1), "executed_flops_per_launch": k_fl / max(k_n, 1),
             "algorithmic_bytes_per_launch": (getattr(eng, "last_tc_bytes", 0.0) / max(tc_n, 1)) if tc_n > 0 else None,
@@ -391,10 +585,19 @@ def main():
     out = None
     if rank == 0:
         rdwt = dwt_roofline(dev, peaks["hbm_gbs"])
-        cpu = None
-        if not args.no_cpu_baseline and not args.wavelet_in_unet:
-            cpu = cpu_baseline(args.cpu_sample_seconds, os.cpu_count() or 1)
-        out = {"metric": "restored images/sec @256x256, 50-step DDIM", "value": value, "unit": "images/s",
+        cpu = parity = gpu_base = None
+        # baselines and the parity block run at N = 1 only: at N > 1 the other ranks would spin in the closing barrier on the
+        # host cores the CPU sample is timed on (and rank 0's GPU would idle through it in the driver's utilisation record)
+        if world == 1 and not args.wavelet_in_unet:
+            del restorer, eng
+            torch.cuda.empty_cache()
+            if not args.no_parity:
+                parity = parity_block(dev)
+            if not args.no_gpu_baseline:
+                gpu_base = gpu_eager_baseline(dev, B if args.config == 2 else 64)
+            if not args.no_cpu_baseline:
+                cpu = cpu_baseline(args.cpu_sample_seconds, os.cpu_count() or 1)
+        out = {"metric": metric_name(), "value": value, "unit": "images/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
@@ -402,7 +605,8 @@ def main():
                "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(x_pin.numel() * 4 + noise_pin.numel() * 4) * world,
                        "d2h_bytes_per_step": int(B * 3 * H * W * 4) * world, "ms_per_step": ms_e2e,
                        "note": "every rank copies its own inputs H2D from pinned memory and its restored images D2H into pinned memory"},
-               "gpu_launches": int(launches), "roofline": roof, "roofline_dwt": rdwt, "cpu_baseline": cpu}
+               "gpu_launches": int(launches), "roofline": roof, "roofline_dwt": rdwt, "cpu_baseline": cpu,
+               "parity": parity, "gpu_eager_baseline": gpu_base}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

@@ -98,6 +98,10 @@ WDM_API int wdm_iwt4x4_cat(const float* lo, int Clo, const float* hi, int Chi, f
 #define WDM_PREC_BF16 1
 /* engine flags (wdm_unet_create) */
 #define WDM_ENGINE_NO_TC 0x1 /* bf16 mode: use the CUDA-core GEMM for every contraction (debug / A-B testing) */
+/* bf16 mode: allow a contraction whose shape the tcgen05 kernel does not tile to run on the CUDA-core kernel. Without
+ * this flag such a shape makes wdm_unet_forward return WDM_ERR_UNSUPPORTED -- there is no silent fallback. (Odd patch
+ * counts are NOT such a shape: the engine pads them internally.) */
+#define WDM_ENGINE_ALLOW_SIMT 0x2
 
 typedef struct wdm_unet_config {
     int ch;             /* model.ch */
@@ -139,6 +143,9 @@ WDM_API int wdm_unet_forward(wdm_unet_t* net, const void* x, const float* t, int
 WDM_API int wdm_unet_profile_enable(wdm_unet_t* net, int on);
 WDM_API int wdm_unet_profile_read(wdm_unet_t* net, double* tc_ms, double* tc_flops, long long* tc_launches,
                                   double* simt_ms, double* simt_flops, long long* simt_launches);
+/* contraction launches since wdm_unet_create, by kernel class: tcgen05 tensor-core / CUDA-core (always counted, also
+ * without profiling). In WDM_PREC_BF16 mode without WDM_ENGINE_NO_TC / WDM_ENGINE_ALLOW_SIMT, *simt stays 0. */
+WDM_API int wdm_unet_counters(const wdm_unet_t* net, long long* tc_launches, long long* simt_launches);
 /* algorithmic HBM bytes (each operand / result tensor counted once) of the tensor-core launches since the last call */
 WDM_API double wdm_unet_profile_tc_bytes(wdm_unet_t* net);
 

@@ -14,6 +14,7 @@ Generates the committed golden vectors under tests/golden/ by importing the UNMO
   * models/restoration.py:63-168    the DWT -> sample -> x0_preds[-5] -> IWT -> clamp sandwich (config #1,
                                     with HFRM bypassed: x_other = HF bands of the DWT of the synthetic
                                     gt)                                      -> sandwich_full.npz
+  * the same sandwich at 50 DDIM steps (BASELINE configs[1], two independent B = 1 runs) -> sandwich_s50.npz
 
 It also checks, while it runs, that the oracle restatements (oracle/unet_oracle.py, oracle/dwt_oracle.c)
 agree with the reference. /root/reference does not exist on the GPU box, so nothing at test time imports
@@ -129,6 +130,53 @@ def golden_hfrm():
           float(y.min()), float(y.max()))
 
 
+def golden_sandwich_s50(ref_unet, ref_wavelet, ref_ddm, ref_metrics):
+    """BASELINE.json configs[1] (the north_star's own parity config: 256x256, **50** DDIM steps, fp32) -> sandwich_s50.npz.
+    The reference sampler is batch-1 only (ddm_wavelet.py:486), so "batch 16" = independent B = 1 runs; two of
+    them are stored (seeds 61 and 62 for the inputs, the SAME seed-61 weights) and the GPU test places them at different
+    slots of a 16-image batch. Per image: x0_preds[-5] (restoration.py:108, the prediction made at t = 80), the full clamped
+    256x256 output of restoration.py:111-135 with the HFRM bypassed (x_other = HF bands of DWT(gt), the `if 0:` branch at
+    :99-100), torchPSNR against the synthetic gt, and the last x_t. The oracle restatement is run on image 0 and must be
+    bit-equal."""
+    cfgF = O.default_config()
+    torch.manual_seed(61)
+    netF = ref_unet.DiffusionUNet(cfgF).eval()
+    sdF = O.init_state_dict(cfgF, seed=61)
+    assert all(torch.equal(sdF[k], v) for k, v in netF.state_dict().items())
+    dec = ref_wavelet.WaveletTransform(scale=2, dec=True)
+    rec = ref_wavelet.WaveletTransform(scale=2, dec=False)
+    betas = O.beta_schedule(cfgF)
+    stubF = types.SimpleNamespace(config=cfgF, num_timesteps=1000, device=torch.device("cpu"))
+    seq = range(0, 1000, 1000 // 50)
+    lats, outs, psnrs, xlast, seeds = [], [], [], [], [61, 62]
+    for n, seed in enumerate(seeds):
+        g = torch.Generator().manual_seed(seed)
+        ximg = torch.rand(1, 6, 256, 256, generator=g)
+        noise = torch.randn(1, 3, 64, 64, generator=g)
+        with torch.no_grad():
+            xa = 2 * ximg - 1.0
+            x_cond = dec(xa[:, :3].contiguous())
+            x_other = dec(xa[:, 3:].contiguous())[:, 3:]
+            with contextlib.redirect_stdout(io.StringIO()):
+                xs, x0p = ref_ddm.DenoisingDiffusion_Wavelet.generalized_steps_overlapping(
+                    stubF, noise, x_cond, seq, netF, betas, eta=0., corners=[(0, 0)], p_size=64, x_other=x_other,
+                    use_other=True)
+            assert len(x0p) == 50
+            lat = x0p[-5]
+            out = torch.clamp((rec(torch.cat([lat[:, :3], x_other], dim=1)) + 1.0) / 2.0, 0.0, 1.0)
+            psnr = ref_metrics.torchPSNR(ximg[:, 3:], out)
+            if n == 0:
+                oxs, ox0p = O.ddim_sample_overlapping(lambda a, tt: O.unet_forward(sdF, cfgF, a, tt), noise, x_cond, x_other,
+                                                      list(seq), betas, [(0, 0)], 64)
+                assert all(torch.equal(a, b) for a, b in zip(x0p, ox0p)), "oracle DDIM (50 steps) != reference"
+        lats.append(lat.numpy()), outs.append(out.numpy()), psnrs.append(float(psnr)), xlast.append(xs[-1].numpy())
+        print(f"  s50 image {n}: psnr {float(psnr):.6f} latent range [{float(lat.min()):.1f}, {float(lat.max()):.1f}] "
+              f"saturated pixels {float(((out == 0) | (out == 1)).float().mean()):.3f}")
+    np.savez(os.path.join(OUT, "sandwich_s50.npz"), seeds=np.array(seeds), steps=50, latent_m5=np.concatenate(lats),
+             out=np.concatenate(outs), psnr=np.array(psnrs, np.float32), xs_last=np.concatenate(xlast))
+    print("sandwich_s50.npz ok")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -138,6 +186,9 @@ def main():
         return
     if "--only-hfrm" in sys.argv:
         golden_hfrm()
+        return
+    if "--only-s50" in sys.argv:
+        golden_sandwich_s50(ref_unet, ref_wavelet, ref_ddm, ref_metrics)
         return
 
     # ---------------------------------------------------------------- DWT / IWT
@@ -279,6 +330,7 @@ def main():
     print("sandwich_full.npz ok; psnr", float(psnr), "latent range", float(lat.min()), float(lat.max()))
     golden_wavelet_in_unet(ref_unet, ref_ddm)
     golden_hfrm()
+    golden_sandwich_s50(ref_unet, ref_wavelet, ref_ddm, ref_metrics)
 
 
 if __name__ == "__main__":

@@ -34,6 +34,7 @@ WDM_WT_IMPL_TMA = 0x20
 WDM_PREC_FP32 = 0
 WDM_PREC_BF16 = 1
 WDM_ENGINE_NO_TC = 0x1
+WDM_ENGINE_ALLOW_SIMT = 0x2
 WDM_GEMM_IMPL_SIMT = 0
 WDM_GEMM_IMPL_TC = 1
 
@@ -77,6 +78,7 @@ def load() -> ctypes.CDLL:
         "wdm_unet_profile_enable": (c_int, [c_void_p, c_int]),
         "wdm_unet_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
         "wdm_unet_profile_tc_bytes": (ctypes.c_double, [c_void_p]),
+        "wdm_unet_counters": (c_int, [c_void_p, c_void_p, c_void_p]),
         "wdm_dwt4x4_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
         "wdm_iwt4x4_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
         "wdm_iwt4x4_cat": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

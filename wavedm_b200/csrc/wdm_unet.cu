@@ -287,6 +287,7 @@ struct wdm_unet {
     };
     std::vector<Span> spans;
     double tc_bytes = 0;  // algorithmic operand/result bytes of the profiled tensor-core launches
+    long long n_tc = 0, n_simt = 0;  // contraction launches since creation, by kernel class (wdm_unet_counters)
     ~wdm_unet() {
         for (auto& s : spans) {
             cudaEventDestroy(s.a);
@@ -474,6 +475,12 @@ struct Ctx {
     Arena* ar;
     cudaStream_t s;
     int P, T;
+    // Odd patch counts (the real RainDrop image is 120x180 -> 45 patches): every activation is ALLOCATED for Pa = P + 1
+    // patches, so the two places that need an even count -- the 8x8 attention (two 64-token patches share a 128-row tile)
+    // and the sub-pixel upsample-conv from an 8x8 grid (phase-major m-tiles) -- run on Pa patches; the slack patch holds
+    // don't-care values that never reach a real patch (rows of a contraction are independent, the softmax is
+    // block-diagonal). No CUDA-core fallback for such shapes.
+    int Pa;
     int st = WDM_OK;
     float* temb = nullptr;   // [T][temb_total]
     float* gn_scratch = nullptr;
@@ -486,7 +493,7 @@ struct Ctx {
 Act new_act(Ctx& c, int H, int W, int C) {
     Act a;
     a.H = H, a.W = W, a.C = C;
-    a.p = c.ar->alloc((size_t)c.P * H * W * C * dtype_size(c.net->dt));
+    a.p = c.ar->alloc((size_t)c.Pa * H * W * C * dtype_size(c.net->dt));
     if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
     return a;
 }
@@ -507,6 +514,12 @@ int run_gemm(Ctx& c, const GemmParams& p) {
     if (c.dry() || c.st != WDM_OK) return c.st;
     int st;
     const bool tc = will_use_tc(c, p);
+    if (!tc && c.net->dt == DT_BF16 && !(c.net->flags & (WDM_ENGINE_NO_TC | WDM_ENGINE_ALLOW_SIMT))) {
+        // bf16 mode never drops to the CUDA-core kernel silently: a shape the tcgen05 kernel does not tile is an error
+        c.fail(WDM_ERR_UNSUPPORTED);
+        return c.st;
+    }
+    (tc ? c.net->n_tc : c.net->n_simt) += 1;
     wdm_unet::Span sp;
     if (c.net->profile) {
         cudaEventCreate(&sp.a);
@@ -598,7 +611,9 @@ Act upsample_conv_subpix(Ctx& c, const Act& a, const ConvSpec& w) {
     p.Hin = a.H, p.Win = a.W, p.Hout = 2 * a.H, p.Wout = 2 * a.W;
     p.taps = 4, p.stride = 1, p.pad = 0, p.ups = 2;
     p.B = w.pw_subpix, p.ldb = 4 * w.Cin, p.b_layout = BL_NK;
-    p.M = c.P * p.Hout * p.Wout, p.N = w.Cout, p.K = 4 * a.C;
+    // phase-major m-tiles of 128 source pixels: a source grid of 64 pixels pairs two patches per tile -> even count (see Ctx::Pa)
+    const int Prun = (a.H * a.W < 128) ? c.Pa : c.P;
+    p.M = Prun * p.Hout * p.Wout, p.N = w.Cout, p.K = 4 * a.C;
     p.alpha = 1.f, p.bias = w.pb;
     p.ldo = w.Cout;
     p.a_dtype = p.b_dtype = p.out_dtype = c.net->dt;
@@ -672,7 +687,8 @@ Act resblock_op(Ctx& c, const Act& x, const Act* x2, const ResSpec& r) {
 Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a, int G) {
     // G patches share one 128-row tile when a patch has fewer than 128 tokens (the 8x8 mid block: G = 2): the matmuls run
     // on groups of G*L rows and the softmax is block-diagonal (cross-patch scores are masked to zero probability).
-    const int C = a.C, L = x.H * x.W, P = c.P, Lg = G * L, Hg = G * x.H;
+    const int C = a.C, L = x.H * x.W, Lg = G * L, Hg = G * x.H;
+    const int P = G > 1 ? c.Pa : c.P;  // G = 2 pairs patches: odd counts run with the slack patch (see Ctx::Pa)
     const size_t es = 2;
     static const int fused_enabled = []() {
         const char* e = getenv("WDM_ATTN_FUSED");
@@ -680,6 +696,12 @@ Act attn_op_tc(Ctx& c, const Act& x, const AttnSpec& a, int G) {
     }();
     const bool fused = fused_enabled && a.gw && a.wpv;  // the four-contraction form (see AttnSpec)
     Act n = gn_op(c, x, nullptr, a.norm, 0);
+    if (P != c.P && !c.dry() && c.st == WDM_OK) {
+        // the slack patch of the normalised input feeds the keys / values of its tile partner's GEMMs as B-operand columns
+        // that the block-diagonal softmax weights with exactly 0: they must be finite (0 * NaN would poison the real patch)
+        cudaError_t e = cudaMemsetAsync((char*)n.p + (size_t)c.P * L * C * es, 0, (size_t)(P - c.P) * L * C * es, c.s);
+        if (e != cudaSuccess) c.fail(wdm_cuda_error((int)e));
+    }
     GemmParams p;
     // fused: g = n G^T + u  [P*L][C];  unfused: qk = n Wqk^T + b  [P*L][2C]
     const int ldq = fused ? C : 2 * C;
@@ -765,7 +787,7 @@ Act attn_op(Ctx& c, const Act& x, const AttnSpec& a) {
     const int C = a.C, L = x.H * x.W, P = c.P;
     if (dt == DT_BF16 && !(c.net->flags & WDM_ENGINE_NO_TC) && (C % 128) == 0) {
         if ((L % 128) == 0) return attn_op_tc(c, x, a, 1);
-        if (L == 64 && (P % 2) == 0) return attn_op_tc(c, x, a, 2);
+        if (L == 64) return attn_op_tc(c, x, a, 2);
     }
     Act n = gn_op(c, x, nullptr, a.norm, 0);
     Act qkv = conv_op(c, n, nullptr, a.qkv, 1, 0, nullptr, nullptr);  // [P*L][3C]
@@ -812,6 +834,7 @@ int forward_impl(wdm_unet* net, Arena* ar, const void* x, const float* t, int T,
     Model& m = net->model;
     Ctx c;
     c.net = net, c.ar = ar, c.s = s, c.P = P, c.T = T;
+    c.Pa = P + (P & 1);
     const int R = m.cfg.resolution, L = m.cfg.n_levels, nrb = m.cfg.num_res_blocks, tc = 4 * m.cfg.ch;
     c.temb = reinterpret_cast<float*>(ar->alloc((size_t)T * m.temb_total * 4));
     float* temb_scratch = reinterpret_cast<float*>(ar->alloc((size_t)T * 2 * tc * 4));
@@ -1063,6 +1086,13 @@ extern "C" int wdm_unet_profile_read(wdm_unet_t* net, double* tc_ms, double* tc_
     if (simt_ms) *simt_ms = ms[1];
     if (simt_flops) *simt_flops = fl[1];
     if (simt_launches) *simt_launches = n[1];
+    return WDM_OK;
+}
+
+extern "C" int wdm_unet_counters(const wdm_unet_t* net, long long* tc_launches, long long* simt_launches) {
+    if (!net) return WDM_ERR_BAD_ARG;
+    if (tc_launches) *tc_launches = net->n_tc;
+    if (simt_launches) *simt_launches = net->n_simt;
     return WDM_OK;
 }
 

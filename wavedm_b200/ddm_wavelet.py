@@ -58,9 +58,15 @@ class EMAHelper(object):
                 self.shadow[name].data = (1. - self.mu) * param.data + self.mu * self.shadow[name].data
 
     def ema(self, module):
-        for name, param in self._unwrap(module).named_parameters():
-            if param.requires_grad:
-                param.data.copy_(self.shadow[name].data)
+        """ddm_wavelet.py:63-66. Written through ``param.copy_`` under no_grad (not ``param.data``) so the tensors' version
+        counters move, and the packed CUDA engine of the module is dropped explicitly: the next forward re-packs."""
+        inner = self._unwrap(module)
+        with torch.no_grad():
+            for name, param in inner.named_parameters():
+                if param.requires_grad:
+                    param.copy_(self.shadow[name].data)
+        if hasattr(inner, "invalidate_engine"):
+            inner.invalidate_engine()
 
     def ema_copy(self, module):
         inner = self._unwrap(module)
@@ -179,6 +185,8 @@ class DenoisingDiffusion_Wavelet(object):
         self.step = checkpoint['step']
         net = self.model.module if hasattr(self.model, "module") else self.model
         net.load_state_dict(checkpoint['state_dict'], strict=True)
+        if hasattr(net, "invalidate_engine"):
+            net.invalidate_engine()
         self.optimizer.load_state_dict(checkpoint['optimizer'])
         self.ema_helper.load_state_dict(checkpoint['ema_helper'])
         if ema:
@@ -261,23 +269,32 @@ class DenoisingDiffusion_Wavelet(object):
                 print(f"starting processing from image {y}")
                 x = x.flatten(start_dim=0, end_dim=1) if x.ndim == 5 else x
                 x_all = data_transform(x.to(self.device))
-                x_cond = self.wavelet_dec(x_all[:, :3].contiguous())
-                x_gt = self.wavelet_dec(x_all[:, 3:].contiguous())
+                wiu = bool(getattr(self.config.data, "wavelet_in_unet", False))
+                x_cond, x_gt = x_all[:, :3].contiguous(), x_all[:, 3:].contiguous()
                 x_other, wd_wav = None, None
-                if cfgm.use_other_channels:
-                    wd = self.generator(x[:, :3].to(self.device))
-                    wd_wav = self.wavelet_dec(data_transform(wd))
-                    x_other = wd_wav[:, cfgm.other_channels_begin:].contiguous()
+                if not wiu:   # ddm_wavelet.py:359-370: with wavelet_in_unet the network does the DWT / IWT itself
+                    x_cond = self.wavelet_dec(x_cond)
+                    x_gt = self.wavelet_dec(x_gt)
+                    if cfgm.use_other_channels:
+                        wd = self.generator(x[:, :3].to(self.device))
+                        wd_wav = self.wavelet_dec(data_transform(wd))
+                        x_other = wd_wav[:, cfgm.other_channels_begin:].contiguous()
                 out_list = self.diffusive_restoration(x_cond, x_other=x_other, r=r, total=total, last=False,
                                                       use_other=cfgm.use_other_channels)
                 x_output = out_list[1][-5].to(self.device)
+                # (the reference leaves x_output_hrgt_cat undefined in wavelet_in_unet mode and raises NameError at :398;
+                # here that panel of the grid shows the restored image again)
                 x_hrgt = x_output
-                if cfgm.pred_channels < cfgm.in_channels:
+                if not wiu and cfgm.pred_channels < cfgm.in_channels and wd_wav is not None:   # :380-384
                     x_hrgt = torch.cat([x_output[:, :cfgm.pred_channels], x_gt[:, cfgm.pred_channels:]], dim=1)
                     x_output = torch.cat([x_output[:, :cfgm.pred_channels], wd_wav[:, cfgm.pred_channels:]], dim=1)
-                x_output = inverse_data_transform(self.wavelet_rec(x_output.contiguous()))
-                x_cond_img = inverse_data_transform(self.wavelet_rec(x_cond))
-                x_hrgt = inverse_data_transform(self.wavelet_rec(x_hrgt.contiguous()))
+                if not wiu:                                                                      # :386-390
+                    x_output = self.wavelet_rec(x_output.contiguous())
+                    x_cond = self.wavelet_rec(x_cond)
+                    x_hrgt = self.wavelet_rec(x_hrgt.contiguous())
+                x_output = inverse_data_transform(x_output)
+                x_cond_img = inverse_data_transform(x_cond)
+                x_hrgt = inverse_data_transform(x_hrgt)
                 gt = x[:, 3:]
                 print("psnr", torchPSNR(gt.to(self.device), x_output))
                 all_samples += [x_cond_img.cpu(), x_hrgt.cpu(), x_output.cpu(), gt]
@@ -306,9 +323,15 @@ class DenoisingDiffusion_Wavelet(object):
                 self.model.train()
                 self.step += 1
                 x = x.to(self.device)
-                x_all = self.all_wavlet_dec(data_transform(x))
+                x_all = data_transform(x)
+                wiu = bool(getattr(cfg.data, "wavelet_in_unet", False))
+                if not wiu:   # ddm_wavelet.py:227: with wavelet_in_unet the model consumes pixel-domain halves (half = 3)
+                    x_all = self.all_wavlet_dec(x_all)
                 half = x_all.shape[1] // 2
                 if cfgm.use_other_channels:
+                    if wiu and not cfgm.use_gt_in_train:
+                        raise NotImplementedError("wavelet_in_unet with use_other_channels and use_gt_in_train=False is "
+                                                  "undefined in the reference (x_output_wdnet_wav is never set, :247)")
                     if cfgm.use_gt_in_train:
                         hf = x_all[:, half:][:, cfgm.other_channels_begin:]
                     else:

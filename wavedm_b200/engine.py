@@ -230,6 +230,12 @@ class UNetEngine:
                                         ctypes.c_float(at_next), _lib.current_stream_ptr(self.device))
         _lib.check(st, "wdm_ddim_step")
 
+    def counters(self):
+        """(tensor-core, CUDA-core) contraction launches since the engine was created."""
+        a, b = ctypes.c_longlong(), ctypes.c_longlong()
+        _lib.check(self.lib.wdm_unet_counters(self.handle, ctypes.byref(a), ctypes.byref(b)), "wdm_unet_counters")
+        return int(a.value), int(b.value)
+
     # ------------------------------------------------------------------------------------------ profiling
     def profile(self, on: bool) -> None:
         self._profiling = bool(on)  # event-bracketed launches cannot be captured into a CUDA graph

@@ -34,6 +34,22 @@ def build_restorer(config, device, sampling_timesteps=50, max_patches=64, seed=6
     rng = torch.random.get_rng_state()
     torch.manual_seed(seed)
     diffusion = DenoisingDiffusion_Wavelet(args, config)
+    # the UNet weights every golden vector was made with: torch.manual_seed(seed); DiffusionUNet(config) ALONE (the
+    # constructor above builds the HFRM first, which advances the generator)
+    seeded_unet_weights(diffusion, seed)
     torch.random.set_rng_state(rng)
     diffusion.model.eval()
     return DiffusiveRestoration(diffusion, args, config)
+
+
+def seeded_unet_weights(diffusion, seed: int = 61) -> None:
+    """Loads ``torch.manual_seed(seed); DiffusionUNet(config).state_dict()`` (PyTorch default init, the reference's own
+    module order) into ``diffusion.model`` -- identical on every rank, so it is consistent with the DDP broadcast."""
+    from .unet import DiffusionUNet
+    rng = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    sd = DiffusionUNet(diffusion.config).state_dict()
+    torch.random.set_rng_state(rng)
+    net = diffusion.model.module if hasattr(diffusion.model, "module") else diffusion.model
+    net.load_state_dict(sd, strict=True)
+    net.invalidate_engine()

@@ -82,7 +82,8 @@ class DiffusiveRestoration:
         net = df.model.module if hasattr(df.model, "module") else df.model
         from .sampler import DdimSampler
         sampler = DdimSampler(net.engine(), max_patches=getattr(self.args, "max_patches", None))
-        xs_hist, x0_hist = sampler.sample(noise, x_cond, x_other if use_other else None, seq, df.betas, corners, p_size)
+        xs_hist, x0_hist = sampler.sample(noise, x_cond, x_other if use_other else None, seq, df.betas, corners, p_size,
+                                          keep_last=5)   # only x0_preds[-5] is read
         latent = x0_hist[-5]                                # restoration.py:108
         out: Dict[str, torch.Tensor] = {"latent": latent, "x_cond_wav": x_cond, "x_gt_wav": x_gt}
         lat = latent[:, :cfgm.pred_channels]
@@ -121,7 +122,7 @@ class DiffusiveRestoration:
         net = df.model.module if hasattr(df.model, "module") else df.model
         from .sampler import DdimSampler
         sampler = DdimSampler(net.engine(), max_patches=getattr(self.args, "max_patches", None))
-        xs_hist, x0_hist = sampler.sample(noise, x_cond, None, seq, df.betas, corners, p_size)
+        xs_hist, x0_hist = sampler.sample(noise, x_cond, None, seq, df.betas, corners, p_size, keep_last=5)
         latent = x0_hist[-5]                                # restoration.py:108
         return {"latent": latent, "output": torch.clamp((latent + 1.0) / 2.0, 0.0, 1.0),
                 "cond": torch.clamp((x_cond + 1.0) / 2.0, 0.0, 1.0)}

@@ -91,10 +91,11 @@ class DdimSampler:
     @torch.no_grad()
     def sample(self, x: torch.Tensor, x_cond: torch.Tensor, x_other: Optional[torch.Tensor], seq: Sequence[int],
                betas: torch.Tensor, corners: Sequence[Tuple[int, int]], p_size: int, eta: float = 0.0,
-               keep_history: bool = True):
+               keep_history: bool = True, keep_last: Optional[int] = None):
         """Returns (xs_hist [S, B, C, h, w], x0_hist [S, B, C, h, w]) device tensors (history of x_{t-1} and
         of the x0 predictions, in sampling order). With keep_history=False only the last entries are kept
-        ([1, B, C, h, w])."""
+        ([1, B, C, h, w]); with keep_last=n only the last n steps ([min(n, S), ...], so that ``x0_hist[-5]`` -- the element
+        restoration.py:108 reads -- needs 5 slots instead of S)."""
         eng = self.engine
         if eta != 0.0:
             raise NotImplementedError("only eta = 0 (deterministic DDIM) is implemented; the reference never "
@@ -118,6 +119,8 @@ class DdimSampler:
         P = patches.shape[0]
         tvals = torch.tensor(list(reversed(seq)), dtype=torch.float32).to(dev)
         nh = S if keep_history else 1
+        if keep_last is not None and keep_history:
+            nh = max(1, min(int(keep_last), S))
         xs_hist = torch.empty((nh, B, Cp, h, w), dtype=torch.float32, device=dev)
         x0_hist = torch.empty((nh, B, Cp, h, w), dtype=torch.float32, device=dev)
         eps = torch.empty((P, eng.out_ch, eng.patch, eng.patch), dtype=torch.float32, device=dev)
@@ -136,12 +139,19 @@ class DdimSampler:
                 n = min(chunk, P - p0)
                 eng.gather([x_cond, xt] + srcs_tail, patches[p0:p0 + n], out=xin[:n])
                 eng.forward_nhwc(xin[:n], t, out=eps[p0:p0 + n])
-            slot = k if keep_history else 0
+            slot = self._slot(k, S, nh)
             eng.ddim_step(eps, patches, first, xt, x0_hist[slot], xs_hist[slot], at, at_next)
             if self.mirror_rng:
                 torch.randn_like(xt)
             xt = xs_hist[slot]
         return xs_hist, x0_hist
+
+    @staticmethod
+    def _slot(k: int, S: int, nh: int) -> int:
+        """History slot of step k when only the last nh of S steps are kept: the kept window is written in order, the steps
+        before it rotate through the same slots (each is overwritten before anyone reads it; x_t of step k lives in the
+        slot step k - 1 wrote, which differs from step k's own slot whenever nh >= 2; nh == 1 updates in place)."""
+        return k if nh == S else (k - (S - nh)) % nh
 
     def _sample_graph(self, x, x_cond, x_other, seq, seq_next, alphas, patches, first, tvals, xs_hist, x0_hist, keep_history):
         eng = self.engine
@@ -158,7 +168,7 @@ class DdimSampler:
         for k, (i_t, j_t) in enumerate(zip(reversed(seq), reversed(seq_next))):
             sg.t.copy_(tvals[k:k + 1])
             sg.graph.replay()
-            slot = k if keep_history else 0
+            slot = self._slot(k, len(seq), x0_hist.shape[0])
             eng.ddim_step(sg.eps, sg.patches, first, sg.xt, x0_hist[slot], xs_hist[slot], float(alphas[i_t + 1]),
                           float(alphas[j_t + 1]))
             if self.mirror_rng:

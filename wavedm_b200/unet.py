@@ -135,6 +135,7 @@ class DiffusionUNet(nn.Module):
         ch, out_ch, ch_mult = m.ch, m.out_ch, tuple(m.ch_mult)
         in_channels = _engine.unet_in_channels(config)
         self.ch, self.temb_ch = ch, ch * 4
+        self.dropout_p = float(m.dropout)
         self.num_resolutions, self.num_res_blocks = len(ch_mult), m.num_res_blocks
         self.resolution, self.in_channels = config.data.image_size, in_channels
         precision = getattr(m, "engine_precision", None)
@@ -193,10 +194,20 @@ class DiffusionUNet(nn.Module):
             raise NotImplementedError("resamp_with_conv=False is not implemented by the engine")
         self._engines = {}
         self._engine_key = None
+        self._engine_gen = 0
 
     # ------------------------------------------------------------------------------------------ engine
     def _param_version(self):
-        return tuple(p._version for p in self.parameters()) + (next(self.parameters()).device,)
+        # version counters catch in-place updates (optimizer.step, load_state_dict, no_grad copy_); writes through
+        # ``param.data`` do NOT bump them, hence the explicit generation counter (invalidate_engine) as well
+        return (self._engine_gen,) + tuple(p._version for p in self.parameters()) + (next(self.parameters()).device,)
+
+    def invalidate_engine(self):
+        """Drop the packed CUDA engine(s): the next inference forward re-packs the current parameter values. Call after
+        writing parameters through ``param.data`` (EMAHelper.ema and load_ddm_ckpt do)."""
+        self._engine_gen += 1
+        self._engines = {}
+        self._engine_key = None
 
     def engine(self, precision=None) -> "_engine.UNetEngine":
         """The CUDA engine for the current parameter values (re-packed when parameters change)."""
@@ -219,8 +230,14 @@ class DiffusionUNet(nn.Module):
         # wavelet_in_unet: pixel-domain [P, 6, 4R, 4R] in, [P, 3, 4R, 4R] out (the reference asserts after its DWT, :351)
         side = self.resolution * (4 if self.use_wavelet_in_unet else 1)
         assert x.shape[2] == x.shape[3] == side
-        if torch.is_grad_enabled() and self.training:
+        # autograd whenever a graph is being recorded (train_diffusion.py, but also eval-mode validation losses or guidance
+        # that differentiate through the network); the engine (bf16 tensor-core by default -- config.model.engine_precision,
+        # "fp32" for the parity mode) only under no_grad / for tensors that need no gradient
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             return self._forward_autograd(x, t)
+        if self.training and self.dropout_p > 0.0:
+            raise NotImplementedError("DiffusionUNet in train() mode under no_grad with dropout > 0: the CUDA engine has no "
+                                      "dropout; call .eval() for inference")
         return self.engine().forward(x, t)
 
     # ------------------------------------------------------------------------------------------ training path
