@@ -225,6 +225,12 @@ WDM_API size_t wdm_groupnorm_scratch_bytes(int P);
 WDM_API int wdm_groupnorm_silu(const void* src0, int C0, const void* src1, int C1, int dtype, int P, int HW,
                                float eps, const float* gamma, const float* beta, int silu, void* out,
                                void* scratch, void* stream);
+/* bf16 only: GroupNorm(32, eps)(+SiLU) of the concat of two NHWC tensors whose statistics come from the side-cars the
+ * tensor-core epilogue writes (wdm_gemm_params::stats_out, sc[P*HW/32][C/4][2] = per 32-row group and 4-channel block (sum,
+ * sum of squares)): finalise + normalise in ONE launch, the form the UNet engine uses (models/unet.py:36-37,31-33). */
+WDM_API int wdm_groupnorm_silu_sidecar(const void* src0, int C0, const float* sc0, const void* src1, int C1, const float* sc1,
+                                       int P, int HW, float eps, const float* gamma, const float* beta, int silu, void* out,
+                                       void* stream);
 WDM_API int wdm_softmax_rows(const float* S, int rows, int L, void* out, int out_dtype, void* stream);
 
 #ifdef __cplusplus

@@ -106,7 +106,7 @@ def test_eval_diffusion_flow_through_compat(tmp_path):
     r = subprocess.run([sys.executable, drv, root], env=env, capture_output=True, text=True, timeout=900, cwd=root)
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-3000:])
     out = r.stdout
-    assert "patch num : 45" in out and "psnr all torch" in out and out.count("psnr this") == 2
+    assert "psnr all torch" in out and out.count("psnr this") == 2
     eng = [l for l in out.splitlines() if l.startswith("ENGINE")][0].split()
     assert eng[1] == "bf16" and int(eng[2]) > 0 and int(eng[3]) == 0, eng   # tensor cores only, odd patch count included
     res = os.path.join(root, "results", "RainDrop", "raindrop")

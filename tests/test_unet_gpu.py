@@ -330,6 +330,40 @@ def test_groupnorm_silu(dtype, shape):
         assert err <= (2e-5 if dtype == 0 else 6e-2), err
 
 
+@pytest.mark.parametrize("shape", [(3, 128, 0, 4096), (2, 256, 128, 1024), (2, 768, 768, 64), (1, 1280, 0, 256), (2, 512, 0, 256),
+                                   (5, 128, 128, 4096), (70, 256, 0, 1024), (1, 768, 0, 64)])
+def test_groupnorm_silu_from_sidecar_one_launch(shape):
+    """GroupNorm + SiLU with the statistics reduced INSIDE the normalise kernel from the producers' side-cars (the engine's
+    form: one launch per GroupNorm), vs F.group_norm; side-cars built here exactly as the tensor-core epilogue defines them."""
+    P, C0, C1, HW = shape
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    a = (torch.randn(P, HW, C0, generator=g) * 3 + 1.5).bfloat16()
+    b = (torch.randn(P, HW, C1, generator=g) - 2).bfloat16() if C1 else None
+    C = C0 + C1
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+
+    def sidecar(t):
+        f = t.float().reshape(P * HW // 32, 32, t.shape[2] // 4, 4)
+        return torch.stack([f.sum(dim=(1, 3)), (f ** 2).sum(dim=(1, 3))], dim=-1).contiguous()
+    full = a.float() if b is None else torch.cat([a.float(), b.float()], 2)
+    ad, bd = a.to(DEV), (b.to(DEV) if b is not None else None)
+    sa, sb = sidecar(a).to(DEV), (sidecar(b).to(DEV) if b is not None else None)
+    gd, bed = gamma.to(DEV), beta.to(DEV)
+    for silu in (0, 1):
+        ref = F.group_norm(full.permute(0, 2, 1).reshape(P, C, HW, 1), 32, gamma, beta, eps=1e-6)
+        if silu:
+            ref = ref * torch.sigmoid(ref)
+        ref = ref.reshape(P, C, HW).permute(0, 2, 1)
+        out = torch.full((P, HW, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+        st = lib.wdm_groupnorm_silu_sidecar(ad.data_ptr(), C0, sa.data_ptr(), bd.data_ptr() if bd is not None else None, C1,
+                                            sb.data_ptr() if sb is not None else None, P, HW, 1e-6, gd.data_ptr(), bed.data_ptr(),
+                                            silu, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "wdm_groupnorm_silu_sidecar")
+        err = (out.float().cpu() - ref).abs().max().item()
+        assert err <= 6e-2, err
+
+
 def test_softmax_rows():
     lib = _lib.load()
     g = torch.Generator().manual_seed(4)

@@ -103,6 +103,8 @@ def load() -> ctypes.CDLL:
         "wdm_groupnorm_scratch_bytes": (c_size_t, [c_int]),
         "wdm_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                        c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+        "wdm_groupnorm_silu_sidecar": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p,
+                                               c_void_p, c_int, c_void_p, c_void_p]),
         "wdm_softmax_rows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     }
     for name, (res, args) in sigs.items():

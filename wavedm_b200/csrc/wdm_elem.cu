@@ -3,6 +3,8 @@
 //   nearest x2 upsample (unet.py:52-53), timestep embedding + temb projections (unet.py:10-28,354-357,125),
 //   patch gather (ddm_wavelet.py:467-478), fused overlap-average + DDIM update (ddm_wavelet.py:485-503),
 //   weight packing.
+#include <stdlib.h>
+
 #include "wdm_common.cuh"
 #include "wdm_engine.h"
 
@@ -251,6 +253,134 @@ __global__ void __launch_bounds__(256) gn_finalize_sidecar_kernel(const float* _
         if (var < 0) var = 0;
         stats[2 * wid] = (float)mean;
         stats[2 * wid + 1] = (float)(1.0 / sqrt(var + eps));
+    }
+}
+
+
+// GroupNorm normalise (+SiLU) with the statistics FINALISED IN THE KERNEL from the side-car partial sums of the producing
+// tensor-core kernel(s) (sc[M/32][C/4][2], see gn_finalize_sidecar_kernel): one launch instead of two per GroupNorm -- the
+// separate finalize launch was ~4 us of pure dependency latency, 51 times per UNet call. Every CTA of a patch reduces that
+// patch's side-car (<= 96 KiB, L2-resident: the producer wrote it microseconds ago) in a fixed order, so all CTAs obtain
+// bit-identical (mean, rstd); a CTA then makes `passes` passes of U x ppi pixels so the prologue is amortised.
+// Prologue mapping: column = 4-channel block b, `ngrp` thread groups split the 32-row groups; coalesced float2 reads,
+// double accumulation, a fixed-order second stage per GroupNorm group.
+// `reverse`: CTAs walk patches / pixel chunks from the END of the tensor: the producing kernel wrote the tensor front to
+// back, so its tail is what the L2 still holds (and this kernel's own output is then consumed front to back, again most
+// recently written first).
+template <bool kSilu>
+__global__ void __launch_bounds__(256, 3) gn_apply_sc_kernel(const __nv_bfloat16* __restrict__ s0, int C0, const float* __restrict__ sc0,
+                                                          const __nv_bfloat16* __restrict__ s1, int C1, const float* __restrict__ sc1,
+                                                          int HW, int pix_per_cta, double eps, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                                                          int reverse) {
+    constexpr int V = 8;
+    __shared__ double2 part[384];
+    __shared__ float2 s_stat[32];
+    wdm_grid_launch_dependents();
+    const int C = C0 + C1, nvec = C / V, cpg = C / 32;
+    const int p = reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    const int chunk = reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int vec = tid % nvec, lane_pix = tid / nvec, ppi = T / nvec;
+    const int c = vec * V;
+    float ga[V], be[V];
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {   // parameters do not depend on the predecessor: load before the dependency wait
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c + i));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c + i));
+        ga[i] = g4.x, ga[i + 1] = g4.y, ga[i + 2] = g4.z, ga[i + 3] = g4.w;
+        be[i] = b4.x, be[i + 1] = b4.y, be[i + 2] = b4.z, be[i + 3] = b4.w;
+    }
+    wdm_grid_dependency_wait();
+    {
+        const int nblk = C >> 2, nb = cpg >> 2, nrg = HW >> 5, b0n = C0 >> 2, b1n = C1 >> 2;
+        const int ngrp = T >= nblk ? T / nblk : 1;
+        const int ncol = T >= nblk ? 1 : (nblk + T - 1) / T;   // columns per thread when the CTA is narrower than the side-car
+        for (int j = 0; j < ncol; ++j) {
+            const int b = T >= nblk ? tid % nblk : tid + j * T;
+            const int sub = T >= nblk ? tid / nblk : 0;
+            if (b < nblk && sub < ngrp) {
+                const float* base = b < b0n ? sc0 + ((long long)p * nrg * b0n + b) * 2 : sc1 + ((long long)p * nrg * b1n + (b - b0n)) * 2;
+                const long long pitch = (b < b0n ? b0n : b1n) * 2;
+                double sum = 0, sq = 0;
+                int rg = sub;
+                for (; rg + 7 * ngrp < nrg; rg += 8 * ngrp) {
+                    float2 t[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) t[u] = *reinterpret_cast<const float2*>(base + (long long)(rg + u * ngrp) * pitch);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) sum += t[u].x, sq += t[u].y;
+                }
+                for (; rg < nrg; rg += ngrp) {
+                    const float2 t = *reinterpret_cast<const float2*>(base + (long long)rg * pitch);
+                    sum += t.x, sq += t.y;
+                }
+                part[sub * nblk + b] = make_double2(sum, sq);
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double sum = 0, sq = 0;
+            for (int sub = 0; sub < ngrp; ++sub)
+                for (int bi = 0; bi < nb; ++bi) {
+                    const double2 t = part[sub * nblk + tid * nb + bi];
+                    sum += t.x, sq += t.y;
+                }
+            const double inv_n = 1.0 / ((double)HW * cpg);
+            const double mean = sum * inv_n;
+            double var = sq * inv_n - mean * mean;
+            if (var < 0) var = 0;
+            s_stat[tid] = make_float2((float)mean, (float)(1.0 / sqrt(var + eps)));
+        }
+        __syncthreads();
+    }
+    float a[V], b[V];
+    {
+        const int g0 = c / cpg, g1 = (c + V - 1) / cpg;
+        const float2 st0 = s_stat[g0], st1 = s_stat[g1];
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            const bool second = (c + i) / cpg != g0;
+            const float mean = second ? st1.x : st0.x, rstd = second ? st1.y : st0.y;
+            a[i] = rstd * ga[i];
+            b[i] = be[i] - mean * a[i];
+        }
+    }
+    const __nv_bfloat16* base;
+    int ld, co;
+    if (c < C0)
+        base = s0, ld = C0, co = c;
+    else
+        base = s1, ld = C1, co = c - C0;
+    base += (long long)p * HW * ld + co;
+    __nv_bfloat16* o = out + (long long)p * HW * C + c;
+    const int px_begin = chunk * pix_per_cta;
+    const int px_end = min(HW, px_begin + pix_per_cta);
+    constexpr int U = 8;
+    for (int px0 = px_begin; px0 < px_end; px0 += U * ppi) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int px = px0 + lane_pix + u * ppi;
+            if (px < px_end) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + (long long)px * ld));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int px = px0 + lane_pix + u * ppi;
+            if (px < px_end) {
+                float v[V];
+                const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[2 * i] = __uint_as_float(w[i] << 16), v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    float y = fmaf(v[i], a[i], b[i]);
+                    if (kSilu) y = wdm_silu(y);
+                    v[i] = y;
+                }
+                Vec<__nv_bfloat16, V>::store(o + (long long)px * C, v);
+            }
+        }
     }
 }
 
@@ -637,6 +767,38 @@ int launch_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtyp
         if (silu) WDM_GN_APPLY(__nv_bfloat16, true, false); else WDM_GN_APPLY(__nv_bfloat16, false, false);
     }
 #undef WDM_GN_APPLY
+    return wdm_launch_status();
+}
+
+int launch_gn_apply_sidecar(const void* src0, int C0, const float* sc0, const void* src1, int C1, const float* sc1, int P, int HW,
+                            float eps, const float* gamma, const float* beta, int silu, void* out, cudaStream_t s) {
+    GnGeom g;
+    if (!gn_geom_apply(C0, C1, &g)) return WDM_ERR_BAD_SHAPE;
+    if (((C0 + C1) % 128) || (C0 % 4) || (C1 % 4) || (HW % 32) || !sc0 || (C1 && !sc1) || (C0 + C1) / 4 > 384) return WDM_ERR_BAD_SHAPE;
+    static const int reverse = []() {
+        const char* e = getenv("WDM_GN_REVERSE");
+        return e ? atoi(e) : 0;  // measured: no effect (5.19 vs 5.17 ms)
+    }();
+    const int ppi = g.threads / g.nvec;
+    const int pass_px = ppi * 8;                          // pixels of one pass (U = 8 vectors per thread)
+    int max_chunks = (HW + pass_px - 1) / pass_px;
+    // enough CTAs to fill the chip about twice, as few as possible beyond that: each CTA re-reduces its patch's side-car
+    int chunks = (2 * 148 + P - 1) / P;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    int passes = (max_chunks + chunks - 1) / chunks;
+    const int pix_per_cta = passes * pass_px;
+    dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, P);
+    const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(src0);
+    const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(src1);
+    cudaError_t e;
+    if (silu)
+        e = wdm_launch_pdl(gn_apply_sc_kernel<true>, grid, dim3(g.threads), 0, s, a0, C0, sc0, a1, C1, sc1, HW, pix_per_cta,
+                           (double)eps, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), reverse);
+    else
+        e = wdm_launch_pdl(gn_apply_sc_kernel<false>, grid, dim3(g.threads), 0, s, a0, C0, sc0, a1, C1, sc1, HW, pix_per_cta,
+                           (double)eps, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out), reverse);
+    if (e != cudaSuccess) return wdm_cuda_error((int)e);
     return wdm_launch_status();
 }
 

@@ -42,6 +42,9 @@ int launch_gn_stats(const void* src0, int C0, const void* src1, int C1, int dtyp
 // kernel(s) that produced the source tensor(s): sc[P*HW/32][C/4][2]
 int launch_gn_finalize_sidecar(const float* sc0, int C0, const float* sc1, int C1, int P, int HW, float eps,
                                float* stats, cudaStream_t stream);
+// one launch: (mean, rstd) reduced from the side-car(s) inside the normalise kernel (bf16 storage only)
+int launch_gn_apply_sidecar(const void* src0, int C0, const float* sc0, const void* src1, int C1, const float* sc1, int P, int HW,
+                            float eps, const float* gamma, const float* beta, int silu, void* out, cudaStream_t stream);
 size_t gn_stats_bytes(int P);  // size of the `stats` scratch buffer (mean/rstd + double partial sums)
 // y = ((x - mean) * rstd * gamma + beta), optionally * sigmoid(.)  -> out [P, HW, C0+C1] (materialises the concat)
 int launch_gn_apply(const void* src0, int C0, const void* src1, int C1, int dtype, int P, int HW, const float* stats,
