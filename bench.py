@@ -62,10 +62,12 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (default 64; 32 for --config 5)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--ddim-steps", type=int, default=None)
-    ap.add_argument("--max-patches", type=int, default=None, help="patches per UNet call (default 64; 160 for --config 5)")
+    ap.add_argument("--max-patches", type=int, default=None, help="patches per UNet call (default 64; 148 for --config 5)")
     ap.add_argument("--wavelet-in-unet", action="store_true",
                     help="NOT the BASELINE config: data.wavelet_in_unet (DWT / IWT inside the network at every DDIM step, "
                          "pixel-domain sampler, out_ch 48); the line is labelled accordingly")
+    ap.add_argument("--bypass-hfrm", action="store_true",
+                    help="round-1 behaviour: skip the HFRM (models/arch.py) in both arms, x_other = HF bands of DWT(gt)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-seconds", type=float, default=15.0)
     ap.add_argument("--no-parity", action="store_true", help="skip the parity block (N = 1 only anyway)")
@@ -80,7 +82,9 @@ def parse():
     if args.ddim_steps is None:
         args.ddim_steps = DDIM_STEPS
     if args.max_patches is None:
-        args.max_patches = 160 if args.config == 5 else 64   # 800 patches per DDIM step = 5 calls of 160
+        # config 5: 800 patches per DDIM step in calls of 148 = one patch per SM: every level's tile count is a whole number
+        # of waves (32x32: 4 pair tiles / patch, 16x16: 2, 8x8: 1/2 with 192-wide N tiles, 64x64: 16 tiles of 256 rows)
+        args.max_patches = 148 if args.config == 5 else 64
     return args
 
 
@@ -150,6 +154,9 @@ def make_cfg(precision, device, wavelet_in_unet=False):
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle arm
+BYPASS_HFRM = False  # set from --bypass-hfrm
+
+
 def cpu_restore_sample(n_images, ddim_steps, threads):
     """The CPU oracle port (oracle/unet_oracle.py + oracle/dwt_oracle.c) of the same path on `n_images` images
     for `ddim_steps` DDIM steps of the DDIM_STEPS-step schedule (overlapping 64x64 patches on the grid_r grid when the
@@ -170,7 +177,14 @@ def cpu_restore_sample(n_images, ddim_steps, threads):
     with torch.no_grad():
         x_cond = torch.from_numpy(DO.dwt(x[:, :3].numpy(), flags=1))
         x_gt = torch.from_numpy(DO.dwt(x[:, 3:].numpy(), flags=1))
-        x_other = x_gt[:, 3:]
+        if BYPASS_HFRM:
+            x_other = x_gt[:, 3:]
+        else:  # restoration.py:94-102: HFRM on the [0, 1] conditioning image, its DWT supplies the high-frequency bands
+            from oracle import hfrm_oracle as HO
+            if not hasattr(cpu_restore_sample, "hsd"):
+                cpu_restore_sample.hsd = HO.fill_params(HO.default_shapes(), SEED)
+            wd = HO.hfrm_forward(cpu_restore_sample.hsd, x[:, :3].contiguous())
+            x_other = torch.from_numpy(DO.dwt(wd.numpy(), flags=1))[:, 3:].contiguous()
         hl, wl = O.overlapping_grid_indices(H // 4, W // 4, 64, GRID_R)
         xs, x0p = O.ddim_sample_overlapping(lambda a, tt: O.unet_forward(sd, cfg, a, tt), noise, x_cond, x_other,
                                             seq_run, betas, [(i, j) for i in hl for j in wl], 64)
@@ -244,7 +258,10 @@ def workload_config(args, torch_version):
                         f"seed-61 default-init weights",
             "global_batch": args.batch * args.gpus, "images_per_gpu": args.batch, "ddim_steps": args.ddim_steps,
             "l2": "inputs+activations per step far exceed L2 (126 MB); weights 313 MB bf16", "torch": torch_version,
-            "hfrm": "bypassed in both arms (x_other = HF bands of DWT(gt))"}
+            "hfrm": ("bypassed in both arms (x_other = HF bands of DWT(gt))" if getattr(args, "bypass_hfrm", False) else
+                     "on in both arms (models/arch.py HFRM once per image at full resolution -> DWT -> x_other and the "
+                     "high-frequency bands of the output, restoration.py:94-135): value and e2e time the whole "
+                     "restore_batch; seeded synthetic HFRM weights")}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -437,6 +454,8 @@ def dwt_roofline(dev, peak):
 
 def main():
     args = parse()
+    global BYPASS_HFRM
+    BYPASS_HFRM = bool(args.bypass_hfrm or args.wavelet_in_unet)
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -482,6 +501,8 @@ def main():
     def step_device():
         if args.wavelet_in_unet:
             return restorer.restore_batch(x_dev, r=GRID_R, noise=noise_dev)["output"]
+        if not args.bypass_hfrm:   # the real restore() path: HFRM engine -> DWT -> x_other / output HF bands
+            return restorer.restore_batch(x_dev, r=GRID_R, noise=noise_dev)["output"]
         xo = restorer.diffusion.wavelet_dec(2 * x_dev[:, 3:].contiguous() - 1.0)[:, 3:].contiguous()
         res = restorer.restore_batch(x_dev, r=GRID_R, noise=noise_dev, x_other=xo)
         return res["output"]
@@ -502,6 +523,8 @@ def main():
         xh = x_pin.to(dev, non_blocking=True)
         nh = noise_pin.to(dev, non_blocking=True)
         if args.wavelet_in_unet:
+            out = restorer.restore_batch(xh, r=GRID_R, noise=nh)["output"]
+        elif not args.bypass_hfrm:
             out = restorer.restore_batch(xh, r=GRID_R, noise=nh)["output"]
         else:
             xo = restorer.diffusion.wavelet_dec(2 * xh[:, 3:].contiguous() - 1.0)[:, 3:].contiguous()
@@ -582,6 +605,26 @@ def main():
     roof["whole_step_algorithmic_tflops"] = e2e_alg_tf
     roof["whole_step_frac"] = e2e_alg_tf / peak_tf
 
+    # the HFRM engine alone (once per image, before the sampling loop): CUDA events around K calls on this batch
+    hfrm = None
+    if not BYPASS_HFRM:
+        gen = restorer.diffusion.generator
+        cond01 = x_dev[:, :3].contiguous()
+        gen(cond01)
+        torch.cuda.synchronize()
+        l1 = lib.wdm_launch_counter()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(3):
+            gen(cond01)
+        e1.record()
+        torch.cuda.synchronize()
+        h_ms = e0.elapsed_time(e1) / 3
+        hfrm = {"ms_per_batch": h_ms, "images": B, "share_of_step": h_ms / ms_per_step,
+                "launches_per_batch": int((lib.wdm_launch_counter() - l1) // 3), "precision": args.precision,
+                "kernel": "hfrm_pw_kernel / hfrm_dw_gate_kernel (csrc/wdm_hfrm.cu)",
+                "note": "models/arch.py HFRM(dim 32, enc [2,2,2,4], mid 6, dec [2,2,2,2]) on the [B,3,H,W] conditioning image"}
+
     out = None
     if rank == 0:
         rdwt = dwt_roofline(dev, peaks["hbm_gbs"])
@@ -606,7 +649,7 @@ def main():
                        "d2h_bytes_per_step": int(B * 3 * H * W * 4) * world, "ms_per_step": ms_e2e,
                        "note": "every rank copies its own inputs H2D from pinned memory and its restored images D2H into pinned memory"},
                "gpu_launches": int(launches), "roofline": roof, "roofline_dwt": rdwt, "cpu_baseline": cpu,
-               "parity": parity, "gpu_eager_baseline": gpu_base}
+               "parity": parity, "gpu_eager_baseline": gpu_base, "hfrm": hfrm}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

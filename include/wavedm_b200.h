@@ -150,6 +150,39 @@ WDM_API int wdm_unet_counters(const wdm_unet_t* net, long long* tc_launches, lon
 WDM_API double wdm_unet_profile_tc_bytes(wdm_unet_t* net);
 
 /* ------------------------------------------------------------------------------------------------
+ * HFRM engine -- the one-shot high-frequency refinement CNN of restore().
+ * Replaces  models/arch.py:206-253  (HFRM.__init__/forward: conv_in, encoder / middle / decoder ResidualBlocks
+ * arch.py:158-204 = LayerNorm2d + 1x1 + depthwise 3x3 + SimpleGate + channel attention + 1x1, 2x2 stride-2 downs,
+ * 1x1 + PixelShuffle ups, conv_out + input residual) at its call site  models/restoration.py:94
+ * (`self.diffusion.generator(x[:, :3])`, also models/ddm_wavelet.py:367).
+ *   x, y : [B, 3, H, W] fp32 NCHW, H and W multiples of 2^n_levels (the reference has no padding path either)
+ * Precision: WDM_PREC_FP32 (fp32 storage, FFMA: parity mode) / WDM_PREC_BF16 (bf16 storage, tensor-core MMAs with fp32
+ * accumulation; LayerNorm statistics, depthwise conv, pooling and channel attention in fp32).
+ * Parameters: ONE flat fp32 device buffer holding the reference's state_dict tensors concatenated in the order reported
+ * by wdm_hfrm_param_info() (names = the reference module's state_dict keys, e.g. "encoders.0.1.conv4.weight").
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct wdm_hfrm_config {
+    int in_channel;      /* 3 */
+    int dim;             /* 32: channels at full resolution, a power of two >= 32 */
+    int mid_blk_num;     /* 6 */
+    int n_levels;        /* len(enc_blk_nums) == len(dec_blk_nums), <= 6 */
+    int enc_blk_nums[8]; /* [2, 2, 2, 4] in models/ddm_wavelet.py:137 */
+    int dec_blk_nums[8]; /* [2, 2, 2, 2] */
+} wdm_hfrm_config;
+
+typedef struct wdm_hfrm wdm_hfrm_t;
+
+WDM_API int wdm_hfrm_param_count(const wdm_hfrm_config* cfg);
+WDM_API int wdm_hfrm_param_info(const wdm_hfrm_config* cfg, int i, char* name, int cap, long long* numel);
+WDM_API size_t wdm_hfrm_packed_bytes(const wdm_hfrm_config* cfg, int precision);
+WDM_API int wdm_hfrm_create(const wdm_hfrm_config* cfg, int precision, const float* flat_params, long long flat_numel,
+                            void* packed, size_t packed_bytes, void* stream, wdm_hfrm_t** out);
+WDM_API void wdm_hfrm_destroy(wdm_hfrm_t* net);
+WDM_API size_t wdm_hfrm_workspace_bytes(const wdm_hfrm_t* net, int B, int H, int W);
+WDM_API int wdm_hfrm_forward(wdm_hfrm_t* net, const float* x, int B, int H, int W, float* y, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Sampler kernels.
  * wdm_gather_patches replaces the crop + cat of  models/ddm_wavelet.py:467-478  (and the NCHW->NHWC
  * conversion of the module-level forward): out[p, y, x, c] = concat_s(src_s)[img_p, c, hi_p+y, wi_p+x],

@@ -176,7 +176,23 @@ def test_hfrm_mirror_vs_reference_golden():
     with torch.no_grad():
         for v in sd.values():
             v.copy_(torch.randn(v.shape, generator=gen) * 0.1)
-        y = net(torch.from_numpy(g["x"]))
+        y = net._forward_autograd(torch.from_numpy(g["x"]))   # the differentiable definition (inference runs the CUDA engine)
     ref = torch.from_numpy(g["y"])
     assert y.shape == ref.shape
     assert (y - ref).abs().max() <= 1e-4 * ref.abs().max()
+    # inference on a CPU module must fail loudly: there is no PyTorch fallback on the restore() path
+    net.requires_grad_(False)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.from_numpy(g["x"]))
+
+
+def test_hfrm_oracle_vs_reference_golden():
+    """oracle/hfrm_oracle.py (functional restatement of models/arch.py:132-253, the checker of the CUDA HFRM engine) against
+    the output of the unmodified reference module (tests/golden/hfrm.npz, generated by oracle/make_golden.py)."""
+    from oracle import hfrm_oracle as HO
+    g = golden("hfrm.npz")
+    shapes = {str(k): [int(v) for v in str(s).split(",")] for k, s in zip(g["keys"], g["shapes"])}
+    sd = HO.fill_params(shapes, int(g["param_seed"]))
+    y = HO.hfrm_forward(sd, torch.from_numpy(g["x"]))
+    ref = torch.from_numpy(g["y"])
+    assert (y - ref).abs().max() <= 2e-5 * ref.abs().max()

@@ -92,6 +92,13 @@ def load() -> ctypes.CDLL:
         "wdm_unet_workspace_bytes": (c_size_t, [c_void_p, c_int]),
         "wdm_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
+        "wdm_hfrm_param_count": (c_int, [c_void_p]),
+        "wdm_hfrm_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, c_void_p]),
+        "wdm_hfrm_packed_bytes": (c_size_t, [c_void_p, c_int]),
+        "wdm_hfrm_create": (c_int, [c_void_p, c_int, c_void_p, c_longlong, c_void_p, c_size_t, c_void_p, c_void_p]),
+        "wdm_hfrm_destroy": (None, [c_void_p]),
+        "wdm_hfrm_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
+        "wdm_hfrm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
         "wdm_gather_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                        c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
         "wdm_gather_patches_dwt": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,

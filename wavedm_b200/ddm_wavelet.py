@@ -149,6 +149,7 @@ class DenoisingDiffusion_Wavelet(object):
         hfrm_path = getattr(args, "hfrm_ckpt", None) or self.HFRM_CKPT
         self.generator.load_state_dict(torch.load(hfrm_path, map_location=self.device), strict=True)
         self.generator.requires_grad_(False)
+        self.generator.engine_precision = getattr(config.model, "engine_precision", None) or "bf16"
 
         self.model = DiffusionUNet(config)
         self.model.to(self.device)
