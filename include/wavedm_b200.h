@@ -150,6 +150,15 @@ WDM_API int wdm_unet_counters(const wdm_unet_t* net, long long* tc_launches, lon
 WDM_API double wdm_unet_profile_tc_bytes(wdm_unet_t* net);
 
 /* ------------------------------------------------------------------------------------------------
+ * restore() metrics. Replaces the three per-image PSNR reductions of  models/restoration.py:142-146  (utils/metrics.py:
+ * 7-11 torchPSNR, :43-51 calculate_psnr_in_GPU(.., True), :53-86 calculate_psnr(.., True)) by one batched launch:
+ *   a, b : [B, 3, H, W] fp32 NCHW;  sse : [B][3] doubles (device) =
+ *   { sum (clamp01(a)-clamp01(b))^2 over 3HW,  sum (Y(a)-Y(b))^2 over HW,  sum (Y(clamp01 a)-Y(clamp01 b))^2 over HW },
+ *   Y = (24.966 c0 + 128.553 c1 + 65.481 c2 + 16) / 255. PSNR = 10 log10(n / sse). Deterministic (fixed-order reduction).
+ * ------------------------------------------------------------------------------------------------ */
+WDM_API int wdm_psnr_stats(const float* a, const float* b, int B, int H, int W, double* sse, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * HFRM engine -- the one-shot high-frequency refinement CNN of restore().
  * Replaces  models/arch.py:206-253  (HFRM.__init__/forward: conv_in, encoder / middle / decoder ResidualBlocks
  * arch.py:158-204 = LayerNorm2d + 1x1 + depthwise 3x3 + SimpleGate + channel attention + 1x1, 2x2 stride-2 downs,

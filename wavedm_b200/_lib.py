@@ -92,6 +92,7 @@ def load() -> ctypes.CDLL:
         "wdm_unet_workspace_bytes": (c_size_t, [c_void_p, c_int]),
         "wdm_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
+        "wdm_psnr_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
         "wdm_hfrm_param_count": (c_int, [c_void_p]),
         "wdm_hfrm_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, c_void_p]),
         "wdm_hfrm_packed_bytes": (c_size_t, [c_void_p, c_int]),

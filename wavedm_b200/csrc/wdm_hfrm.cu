@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(kPwThreads, 2) hfrm_pw_ring_kernel(const PwPar
 // -- a private 4-stage cp.async ring for the activations, a private fp32 patch for the coalesced stores, __syncwarp only (no
 // CTA-wide barrier after the weight load). LayerNorm in the epilogue as in hfrm_pw_ring_kernel; the row statistics never
 // leave registers (the lanes that copied a row are the lanes whose accumulators need it, or one shuffle away).
-constexpr int kStripPatchLd = 68;
+constexpr int kStripPatchLd = 72;  // 72 % 32 == 8: the 64-bit fragment stores of a half-warp hit 32 distinct banks
 template <int K>
 struct StripCfg {
     static constexpr int kLd = K + 8;                                   // bf16 elements per smem row
@@ -765,13 +765,13 @@ __global__ void __launch_bounds__(256) hfrm_pw_strip_kernel(const PwParams p, lo
                     mma_bf16(c1, a[ks], b[2], b[3]);
                 }
             }
-            // ---- fragments -> this warp's fp32 patch (+ LayerNorm algebra, bias, SimpleGate)
+            // ---- fragments -> this warp's fp32 patch (+ LayerNorm algebra, bias, SimpleGate), 64-bit shared accesses
 #pragma unroll
             for (int np = 0; np < 4; ++np) {
                 const int c = n0 + 16 * np + 2 * s;
                 if (c >= p.N) continue;
-                const float bv[4] = {bias_s[c], bias_s[c + 1], bias_s[c + 8], bias_s[c + 9]};
-                const float wv[4] = {wsum_s[c], wsum_s[c + 1], wsum_s[c + 8], wsum_s[c + 9]};
+                const float2 bf = *reinterpret_cast<const float2*>(bias_s + c), bg = *reinterpret_cast<const float2*>(bias_s + c + 8);
+                const float2 wf = *reinterpret_cast<const float2*>(wsum_s + c), wg = *reinterpret_cast<const float2*>(wsum_s + c + 8);
 #pragma unroll
                 for (int hr = 0; hr < 2; ++hr) {
                     const int row = g + 8 * hr;
@@ -779,18 +779,15 @@ __global__ void __launch_bounds__(256) hfrm_pw_strip_kernel(const PwParams p, lo
                     float g0 = acc[(np * 2 + 1) * 4 + 2 * hr], g1 = acc[(np * 2 + 1) * 4 + 2 * hr + 1];
                     if (p.pro == PRO_LN) {
                         const float mu = hr ? mu1 : mu0, rs = hr ? rs1 : rs0;
-                        f0 = rs * (f0 - mu * wv[0]), f1 = rs * (f1 - mu * wv[1]);
-                        g0 = rs * (g0 - mu * wv[2]), g1 = rs * (g1 - mu * wv[3]);
+                        f0 = rs * (f0 - mu * wf.x), f1 = rs * (f1 - mu * wf.y);
+                        g0 = rs * (g0 - mu * wg.x), g1 = rs * (g1 - mu * wg.y);
                     }
-                    f0 += bv[0], f1 += bv[1], g0 += bv[2], g1 += bv[3];
+                    f0 += bf.x, f1 += bf.y, g0 += bg.x, g1 += bg.y;
                     if (gate) {
-                        patch[row * kStripPatchLd + 8 * np + 2 * s] = f0 * g0;
-                        patch[row * kStripPatchLd + 8 * np + 2 * s + 1] = f1 * g1;
+                        *reinterpret_cast<float2*>(patch + row * kStripPatchLd + 8 * np + 2 * s) = make_float2(f0 * g0, f1 * g1);
                     } else {
-                        patch[row * kStripPatchLd + 16 * np + 2 * s] = f0;
-                        patch[row * kStripPatchLd + 16 * np + 2 * s + 1] = f1;
-                        patch[row * kStripPatchLd + 16 * np + 8 + 2 * s] = g0;
-                        patch[row * kStripPatchLd + 16 * np + 8 + 2 * s + 1] = g1;
+                        *reinterpret_cast<float2*>(patch + row * kStripPatchLd + 16 * np + 2 * s) = make_float2(f0, f1);
+                        *reinterpret_cast<float2*>(patch + row * kStripPatchLd + 16 * np + 8 + 2 * s) = make_float2(g0, g1);
                     }
                 }
             }
@@ -815,8 +812,7 @@ __global__ void __launch_bounds__(256) hfrm_pw_strip_kernel(const PwParams p, lo
             for (int it = 0; it < 4; ++it) {
                 if (om[it] < 0) continue;
                 float v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = patch[pr[it] * kStripPatchLd + pc[it] + q];
+                load8(patch + pr[it] * kStripPatchLd + pc[it], v);
                 if (p.epi == EPI_RES) {
                     const uint32_t w4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
 #pragma unroll

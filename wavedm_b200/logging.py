@@ -7,8 +7,8 @@ import torch
 def save_image(img, file_directory, normalize=False):
     import torchvision.utils as tvu
     d = os.path.dirname(file_directory)
-    if d and not os.path.exists(d):
-        os.makedirs(d)
+    if d:
+        os.makedirs(d, exist_ok=True)   # restore() calls this from several PNG worker threads
     tvu.save_image(img, file_directory, normalize=normalize)
 
 

@@ -1,7 +1,33 @@
 """The parity metric and the PSNR variants ``restore()`` prints (``utils/metrics.py:7-11,43-86``).
-Not accelerated (scalar reductions once per image)."""
+
+``psnr_batch`` computes all three variants for a whole batch of image pairs in ONE kernel launch
+(``wdm_psnr_stats``, csrc/wdm_metrics.cu) -- what ``DiffusiveRestoration.restore`` uses; the torch / numpy definitions
+below are the reference-shaped API (``utils.torchPSNR`` etc.) and what the tests compare the kernel with."""
+import math
+
 import numpy as np
 import torch
+
+
+def psnr_batch(a: torch.Tensor, b: torch.Tensor):
+    """a, b: [B, 3, H, W] fp32 CUDA tensors. Returns three float lists (one entry per image):
+    torchPSNR(a, b), calculate_psnr_in_GPU(a, b, True), calculate_psnr(u8(a), u8(b), True) -- restoration.py:142-146."""
+    from . import _lib
+    assert a.shape == b.shape and a.ndim == 4 and a.shape[1] == 3
+    if not a.is_cuda:
+        raise RuntimeError("psnr_batch needs CUDA tensors (no CPU fallback; use torchPSNR / calculate_psnr on the host)")
+    a = a.to(torch.float32).contiguous()
+    b = b.to(device=a.device, dtype=torch.float32).contiguous()
+    B, _, H, W = a.shape
+    sse = torch.empty(B, 3, dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device):
+        st = _lib.load().wdm_psnr_stats(a.data_ptr(), b.data_ptr(), B, H, W, sse.data_ptr(), _lib.current_stream_ptr(a.device))
+    _lib.check(st, "wdm_psnr_stats")
+    s = sse.cpu().tolist()
+
+    def db(x, n):
+        return float("inf") if x == 0 else 10.0 * math.log10(n / x)
+    return ([db(r[0], 3 * H * W) for r in s], [db(r[1], H * W) for r in s], [db(r[2], H * W) for r in s])
 
 
 def torchPSNR(tar_img, prd_img):
