@@ -60,7 +60,9 @@ def parse():
                     help="BASELINE.json configs index + 0: 2 = batch 64/GPU, 256x256, 50 DDIM steps (the metric's config); "
                          "5 = configs[4]: 512x512, 25 patches/image (grid_r 16), 100 DDIM steps, 32 images/GPU")
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (default 64; 32 for --config 5)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32_ffma"],
+                    help="bf16 = tcgen05 throughput mode; fp32 = parity mode on the tensor cores (3-way bf16 split); fp32_ffma = parity "
+                         "mode on CUDA cores")
     ap.add_argument("--ddim-steps", type=int, default=None)
     ap.add_argument("--max-patches", type=int, default=None, help="patches per UNet call (default 64; 148 for --config 5)")
     ap.add_argument("--wavelet-in-unet", action="store_true",
@@ -265,7 +267,7 @@ def workload_config(args, torch_version):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def parity_block(dev, precisions=("fp32", "bf16"), batch=16, slots=(3, 12)):
+def parity_block(dev, precisions=("fp32", "fp32_ffma", "bf16"), batch=16, slots=(3, 12)):
     """The north_star's own parity config (BASELINE.json configs[1]: batch 16, 256x256, 50 DDIM steps, fp32; gates
     |PSNR_new - PSNR_ref| < 0.01 dB and per-pixel |d| < 1e-3 on the element restore() returns, restoration.py:106-135)
     through the public API, against tests/golden/sandwich_s50.npz -- two independent B = 1 runs of the UNMODIFIED reference

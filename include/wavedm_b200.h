@@ -102,6 +102,11 @@ WDM_API int wdm_iwt4x4_cat(const float* lo, int Clo, const float* hi, int Chi, f
  * this flag such a shape makes wdm_unet_forward return WDM_ERR_UNSUPPORTED -- there is no silent fallback. (Odd patch
  * counts are NOT such a shape: the engine pads them internally.) */
 #define WDM_ENGINE_ALLOW_SIMT 0x2
+/* fp32 mode: run the contractions on the tcgen05 kernel through the 3-way bf16 operand split (six bf16 products per
+ * element pair accumulate in fp32 in TMEM: x*w = (x0+x1+x2)(w0+w1+w2) minus the three terms below 2^-24) instead of
+ * CUDA-core FFMA. Storage, GroupNorm, softmax, residuals stay fp32. Shapes the tensor-core kernel does not tile (conv_in's
+ * 96 channels, the attention bmm's, conv_out) stay on the FFMA kernel. */
+#define WDM_ENGINE_TC32 0x4
 
 typedef struct wdm_unet_config {
     int ch;             /* model.ch */
@@ -259,10 +264,27 @@ typedef struct wdm_gemm_params {
      * bias / residual (the P.V product that consumes those probabilities). */
     float* row_scale_out;
     const float* row_scale;
+    /* tensor-core path, fp32 emulation ("tc32"): a_split3 != 0 means src0 is the 3-way bf16 split of an fp32 tensor, laid out
+     * [rows][3*C0] = [hi | mid | lo] with x ~= hi + mid + lo (each piece the bf16 rounding of the remainder), ld0 its row
+     * pitch, and B the matching 6-product arrangement of the split weights [N][taps][6][C0] =
+     * (w_hi, w_mid, w_hi, w_mid, w_lo, w_hi) that pair with the A pieces (hi, hi, mid, mid, hi, lo): K = taps*6*C0,
+     * out_dtype must be fp32. Built by wdm_split3_act / wdm_split3_weight. a_split3 == 2: the same without the dominant
+     * (hi, hi) product, B = [N][taps][5][C0], K = taps*5*C0 -- the executor runs that product as a second plain launch whose
+     * epilogue adds this result (the accumulator truncates on every add: five sixths of the truncations then happen on a
+     * sum 2^-8 of the result). B3 / B3m are used by the UNet executor only (the split weights of a convolution whose `B`
+     * holds the fp32 weights: five small products / dominant product). */
+    int a_split3;
+    const void* B3;
+    const void* B3m;
 } wdm_gemm_params;
 #define WDM_GEMM_IMPL_SIMT 0
 #define WDM_GEMM_IMPL_TC 1
 WDM_API int wdm_gemm(const wdm_gemm_params* p, int impl, void* stream);
+/* tc32 helpers (unit tests; the executor calls the same kernels): split an fp32 matrix (two channel-concatenated sources)
+ * into [rows][3*(C0+C1)] bf16 pieces / a packed fp32 weight matrix [N][taps][C] into [N][taps][6][C] bf16. */
+WDM_API int wdm_split3_act(const float* src0, int C0, const float* src1, int C1, long long rows, void* out, void* stream);
+/* out_main == NULL: out = [N][taps][6][C]; else out_main = [N][taps][C] (w_hi) and out = [N][taps][5][C] */
+WDM_API int wdm_split3_weight(const float* w, int N, int taps, int C, void* out, void* out_main, void* stream);
 WDM_API size_t wdm_groupnorm_scratch_bytes(int P);
 WDM_API int wdm_groupnorm_silu(const void* src0, int C0, const void* src1, int C1, int dtype, int P, int HW,
                                float eps, const float* gamma, const float* beta, int silu, void* out,

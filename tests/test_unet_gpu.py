@@ -32,7 +32,8 @@ class GemmParams(ctypes.Structure):
         [(n, ctypes.c_int) for n in ("ldo", "a_dtype", "b_dtype", "out_dtype")] + [("stats_out", ctypes.c_void_p), ("a_shared", ctypes.c_int), ("tail_1x1", ctypes.c_int),
                                                                                 ("src2", ctypes.c_void_p), ("C2", ctypes.c_int), ("ld2", ctypes.c_int),
                                                                                 ("fuse_softmax", ctypes.c_int), ("softmax_seg", ctypes.c_int), ("out_nchw_valid", ctypes.c_int),
-                                                                                ("row_scale_out", ctypes.c_void_p), ("row_scale", ctypes.c_void_p)]
+                                                                                ("row_scale_out", ctypes.c_void_p), ("row_scale", ctypes.c_void_p),
+                                                                                ("a_split3", ctypes.c_int), ("B3", ctypes.c_void_p), ("B3m", ctypes.c_void_p)]
 
 
 def run_conv(x, x2, w, bias, stride, ups, temb, residual, dtype, impl, want_stats=False):
@@ -633,3 +634,126 @@ def test_gemm_tc_fused_softmax_epilogue(case, deferred):
                 assert (blk - want).abs().max().item() <= 6e-3, (a, b)
             else:
                 assert not blk.any()   # block-diagonal: other patches of the group get probability zero
+
+
+# ---------------------------------------------------------------------------------------------- tc32 (fp32 on the tensor cores)
+TC32_CASES = [
+    # P, C, Cout, H, k, stride, subpix, temb_rows, residual
+    (2, 128, 128, 16, 3, 1, False, 2, True),     # halo macro-stage kernel (Cout = 128 3x3)
+    (2, 256, 256, 16, 3, 1, False, 1, False),    # CTA-pair kernel
+    (2, 128, 128, 16, 3, 2, False, 0, False),    # downsample
+    (3, 192, 384, 8, 1, 1, False, 0, True),      # 1x1 (odd patch count, 192-wide pair tiles)
+    (2, 128, 256, 8, 3, 1, True, 0, False),      # nearest x2 upsample + 3x3 as four sub-pixel phases
+]
+
+
+@pytest.mark.parametrize("case", TC32_CASES)
+def test_gemm_tc32_split_matches_fp32_conv(case):
+    """WDM_ENGINE_TC32's contraction: 3-way bf16 split of both fp32 operands, six products per tap on the tcgen05 kernel with
+    fp32 accumulation -- against the fp64 convolution, next to what the CUDA-core fp32 kernel achieves on the same problem."""
+    P, C, Cout, H, k, stride, subpix, trows, use_res = case
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(1234 + C + Cout)
+    x = torch.randn(P, C, H, H, generator=g)
+    w = torch.randn(Cout, C, k, k, generator=g) / (C * k * k) ** 0.5
+    bias = torch.randn(Cout, generator=g)
+    temb = torch.randn(trows, Cout, generator=g) if trows else None
+    Ho = H * 2 if subpix else (H // 2 if stride == 2 else H)
+    res = torch.randn(P, Cout, Ho, Ho, generator=g) if use_res else None
+    ref = ref_conv(x.double(), None, w.double(), bias.double(), stride, 1 if subpix else 0, None if temb is None else temb.double(),
+                   None if res is None else res.double())
+    st = torch.cuda.current_stream().cuda_stream
+    xa = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    xs = torch.empty(P * H * H, 3 * C, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.wdm_split3_act(xa.data_ptr(), C, 0, 0, P * H * H, xs.data_ptr(), st), "wdm_split3_act")
+    # the three pieces reproduce the fp32 values to 2^-24
+    rec = xs.float().view(-1, 3, C).sum(1)
+    assert float((rec - xa.view(-1, C)).abs().max()) <= 2.0 ** -23 * float(xa.abs().max())
+    if subpix:
+        # pre-summed phase weights (fp32): phase (py, px) tap (ty, tx) sums the 3x3 taps that land on the same source pixel
+        sets = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+        wp = torch.zeros(4, Cout, 4, C)
+        for py in range(2):
+            for px in range(2):
+                for ty in range(2):
+                    for tx in range(2):
+                        for dy in sets[py][ty]:
+                            for dx in sets[px][tx]:
+                                wp[py * 2 + px, :, ty * 2 + tx] += w[:, :, dy, dx]
+        wflat, rows, taps = wp.reshape(4 * Cout, 4 * C).contiguous().to(DEV), 4 * Cout, 4
+    else:
+        taps = k * k
+        wflat, rows = w.permute(0, 2, 3, 1).reshape(Cout, taps * C).contiguous().to(DEV), Cout
+    ws = torch.empty(rows, taps * 6 * C, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.wdm_split3_weight(wflat.data_ptr(), rows, taps, C, ws.data_ptr(), 0, st), "wdm_split3_weight")
+    ws5 = torch.empty(rows, taps * 5 * C, dtype=torch.bfloat16, device=DEV)
+    wsm = torch.empty(rows, taps * C, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib.wdm_split3_weight(wflat.data_ptr(), rows, taps, C, ws5.data_ptr(), wsm.data_ptr(), st), "wdm_split3_weight")
+    b = bias.to(DEV)
+    keep = [b]
+    tb = r = None
+    if temb is not None and not subpix:
+        tb = temb.contiguous().to(DEV)
+    if res is not None and not subpix:
+        r = res.permute(0, 2, 3, 1).contiguous().to(DEV)
+
+    def launch(B, split, kf, a_c0, out_t, bias_t, temb_t, res_t):
+        p = GemmParams()
+        p.src0, p.C0, p.ld0 = xs.data_ptr(), a_c0, 3 * C
+        p.Hin, p.Win, p.Hout, p.Wout = H, H, Ho, Ho
+        p.taps, p.stride, p.pad, p.ups = taps, stride, (1 if k == 3 and stride == 1 and not subpix else 0), (2 if subpix else 0)
+        p.B, p.ldb, p.b_layout = B.data_ptr(), taps * kf * C, 0
+        p.M, p.N, p.K, p.alpha = P * Ho * Ho, Cout, taps * kf * C, 1.0
+        if bias_t is not None:
+            p.bias = bias_t.data_ptr()
+        if temb_t is not None:
+            p.temb, p.temb_rows, p.temb_ld = temb_t.data_ptr(), trows, Cout
+        if res_t is not None:
+            p.residual, p.ldr = res_t.data_ptr(), Cout
+        p.out, p.ldo = out_t.data_ptr(), Cout
+        p.a_dtype = p.b_dtype = 1
+        p.out_dtype = 0
+        p.a_split3 = split
+        _lib.check(lib.wdm_gemm(ctypes.byref(p), _lib.WDM_GEMM_IMPL_TC, st), f"wdm_gemm tc32 split={split}")
+
+    if subpix:
+        ref = ref_conv(x.double(), None, w.double(), bias.double(), 1, 1, None, None)
+    # (a) all six products in one accumulator
+    out6 = torch.empty(P, Ho, Ho, Cout, device=DEV)
+    launch(ws, 1, 6, C, out6, b, tb, r)
+    # (b) the engine's form: five small products (+ bias, temb, residual), then the dominant product + that result
+    tmp = torch.empty(P, Ho, Ho, Cout, device=DEV)
+    out = torch.empty(P, Ho, Ho, Cout, device=DEV)
+    launch(ws5, 2, 5, C, tmp, b, tb, r)
+    launch(wsm, 0, 1, C, out, None, None, tmp)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    err6 = float((out6.permute(0, 3, 1, 2).cpu().double() - ref).abs().max()) / scale
+    err = float((out.permute(0, 3, 1, 2).cpu().double() - ref).abs().max()) / scale
+    # the CUDA-core fp32 kernel on the same problem
+    simt = run_conv(x, None, w, bias, stride, 1 if subpix else 0, None if subpix else temb, None if subpix else res, 0,
+                    _lib.WDM_GEMM_IMPL_SIMT).double()
+    err_simt = float((simt - ref).abs().max()) / scale
+    print(f"tc32 {case}: max rel err two launches {err:.2e}, one accumulator {err6:.2e} (CUDA-core fp32 kernel {err_simt:.2e})")
+    assert err6 <= 3e-5, err6
+    assert err <= 4e-6, err
+
+
+def test_unet_fp32_engine_uses_tensor_cores_and_matches_ffma_engine():
+    """precision='fp32' runs WDM_ENGINE_TC32 by default: tcgen05 launches in the parity mode, output equal to the pure FFMA
+    engine (WDM_ENGINE_NO_TC) to fp32 rounding, and the reference golden still holds (test_unet_full_fp32_vs_reference_golden)."""
+    cfg = O.default_config()
+    sd = O.init_state_dict(cfg, seed=61)
+    x = torch.randn(3, 96, 64, 64, generator=torch.Generator().manual_seed(4))
+    t = torch.tensor([321.0])
+    e32 = engine.UNetEngine(cfg, sd, DEV, precision="fp32")
+    assert e32.flags & _lib.WDM_ENGINE_TC32
+    y = e32.forward(x, t).cpu()
+    tc, simt = e32.counters()
+    assert tc >= 60 and simt <= 16, (tc, simt)   # conv_in, conv_out's fallback and the attention bmm's stay on CUDA cores
+    eff = engine.UNetEngine(cfg, sd, DEV, precision="fp32", flags=_lib.WDM_ENGINE_NO_TC)
+    yf = eff.forward(x, t).cpu()
+    assert eff.counters()[0] == 0
+    rel = float((y - yf).abs().max()) / float(yf.abs().max())
+    print(f"fp32 engine: tc32 vs FFMA max rel diff {rel:.2e}; launches tc {tc} simt {simt}")
+    assert rel <= 2e-5

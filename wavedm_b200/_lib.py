@@ -35,6 +35,7 @@ WDM_PREC_FP32 = 0
 WDM_PREC_BF16 = 1
 WDM_ENGINE_NO_TC = 0x1
 WDM_ENGINE_ALLOW_SIMT = 0x2
+WDM_ENGINE_TC32 = 0x4
 WDM_GEMM_IMPL_SIMT = 0
 WDM_GEMM_IMPL_TC = 1
 
@@ -92,6 +93,8 @@ def load() -> ctypes.CDLL:
         "wdm_unet_workspace_bytes": (c_size_t, [c_void_p, c_int]),
         "wdm_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
+        "wdm_split3_act": (c_int, [c_void_p, c_int, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
+        "wdm_split3_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
         "wdm_psnr_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
         "wdm_hfrm_param_count": (c_int, [c_void_p]),
         "wdm_hfrm_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, c_void_p]),

@@ -892,4 +892,72 @@ int launch_pack_conv_weight(const float* w, int Cout, int Cin, int taps, int Cin
     return wdm_launch_status();
 }
 
+// ------------------------------------------------------------------------------------------------ tc32 operand split
+// fp32 -> three bf16 pieces: p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1) (the subtractions are exact in fp32),
+// x = p0 + p1 + p2 up to 2^-24 |x|. The tensor-core kernel accumulates the six products
+//   x0 w0 + x0 w1 + x1 w0 + x1 w1 + x0 w2 + x2 w0
+// in fp32 (every bf16 x bf16 product is exact in fp32); the dropped terms x1 w2, x2 w1, x2 w2 are <= 2^-24 relative, i.e.
+// at the rounding level of an fp32 FFMA chain. See GemmParams::a_split3 / a_chunk() in wdm_gemm_tc.cu.
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
+    p0 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(p0);
+    p1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(p1);
+    p2 = __float2bfloat16_rn(r2);
+}
+
+// out[row][piece * C + c] for the channel concat of up to two fp32 sources, C = C0 + C1 (both multiples of 4)
+__global__ void __launch_bounds__(256) split3_act_kernel(const float* __restrict__ s0, int C0, const float* __restrict__ s1, int C1,
+                                                        long long rows, __nv_bfloat16* __restrict__ out) {
+    const int C = C0 + C1, cq = C >> 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cq) return;
+    const long long row = i / cq;
+    const int c = (int)(i - row * cq) * 4;
+    const float4 v = c < C0 ? *reinterpret_cast<const float4*>(s0 + row * C0 + c) : *reinterpret_cast<const float4*>(s1 + row * C1 + (c - C0));
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 q[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split3(x[j], q[0][j], q[1][j], q[2][j]);
+#pragma unroll
+    for (int pc = 0; pc < 3; ++pc)
+        *reinterpret_cast<uint2*>(out + row * 3 * C + pc * C + c) = *reinterpret_cast<const uint2*>(q[pc]);
+}
+
+// w: fp32 [N][taps][C] (K-major packed rows) -> out bf16 [N][taps][6][C], product order (w0, w1, w0, w1, w2, w0);
+// with out_main: the dominant product apart -- out_main [N][taps][C] = w0 and out [N][taps][5][C] = (w1, w0, w1, w2, w0)
+__global__ void __launch_bounds__(256) split3_weight_kernel(const float* __restrict__ w, long long total, int C,
+                                                           __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_main) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long nt = i / C;  // (n, tap) row
+    const int c = (int)(i - nt * C);
+    __nv_bfloat16 q[3];
+    split3(w[i], q[0], q[1], q[2]);
+    if (out_main) {
+        out_main[i] = q[0];
+        __nv_bfloat16* o = out + nt * 5 * C + c;
+        o[0] = q[1], o[C] = q[0], o[2 * C] = q[1], o[3 * C] = q[2], o[4 * C] = q[0];
+    } else {
+        __nv_bfloat16* o = out + nt * 6 * C + c;
+        o[0] = q[0], o[C] = q[1], o[2 * C] = q[0], o[3 * C] = q[1], o[4 * C] = q[2], o[5 * C] = q[0];
+    }
+}
+
+int launch_split3_act(const float* src0, int C0, const float* src1, int C1, long long rows, void* out, cudaStream_t s) {
+    if (!src0 || !out || C0 <= 0 || (C0 % 4) || (C1 % 4) || (C1 && !src1)) return WDM_ERR_BAD_SHAPE;
+    if (rows <= 0) return WDM_OK;
+    const long long n = rows * ((C0 + C1) / 4);
+    split3_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src0, C0, src1, C1, rows, reinterpret_cast<__nv_bfloat16*>(out));
+    return wdm_launch_status();
+}
+
+int launch_split3_weight(const float* w, int N, int taps, int C, void* out, void* out_main, cudaStream_t s) {
+    if (!w || !out || N <= 0 || taps <= 0 || C <= 0) return WDM_ERR_BAD_SHAPE;
+    const long long total = (long long)N * taps * C;
+    split3_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w, total, C, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                        reinterpret_cast<__nv_bfloat16*>(out_main));
+    return wdm_launch_status();
+}
+
 }  // namespace wdm

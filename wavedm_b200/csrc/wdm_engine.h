@@ -108,6 +108,11 @@ int launch_ddim_step(const DdimParams& p, cudaStream_t stream);
 int launch_pack_conv_weight(const float* w, int Cout, int Cin, int taps, int Cin_pad, void* out, int out_dtype,
                             long long ldk, long long k_off, cudaStream_t stream);
 
+// tc32 (fp32 contractions on the tensor cores through a 3-way bf16 split, see wdm_elem.cu / GemmParams::a_split3)
+int launch_split3_act(const float* src0, int C0, const float* src1, int C1, long long rows, void* out, cudaStream_t stream);
+// out_main == null: [N][taps][6][C]; else the dominant product apart: out_main [N][taps][C], out [N][taps][5][C]
+int launch_split3_weight(const float* w, int N, int taps, int C, void* out, void* out_main, cudaStream_t stream);
+
 int launch_vec_add(const float* a, const float* b, float* out, int n, cudaStream_t stream);
 // pack-time C x C fp32 products: mode 0 out = X^T Y, mode 1 out = X Y; matvec: out = X^T v / X v (+ add)
 int launch_matmul_cc(const float* X, const float* Y, float* out, int C, int mode, cudaStream_t stream);

@@ -75,7 +75,23 @@ struct TcArgs {
     const float* row_scale;    // per-row factor applied to the accumulator (the P.V product after such a softmax)
     int epi_tma;               // bf16 results (and the residual) move through shared memory with TMA stores / loads
     int Wsrc;                  // subpix: source-grid width (epi_tma store box geometry)
+    int split_cpp;             // tc32: 64-channel chunks per bf16 piece of segment 0 (0 = plain operands), see a_chunk()
+    uint32_t split_tab;        // tc32: A piece of product pr in nibble pr
 };
+
+// tc32 (fp32 emulated by a 3-way bf16 split, GemmParams::a_split3): the K loop of a tap walks SIX products
+// (A piece, B piece) = (hi,hi) (hi,mid) (mid,hi) (mid,mid) (hi,lo) (lo,hi); the weights are packed in exactly that order, the
+// activation tensor holds its three pieces side by side ([hi | mid | lo] channels), so only the A coordinate needs a map:
+// virtual chunk kc = product * cpp + c  ->  chunk (piece(product) * cpp + c) of the split tensor.
+// a_split3 == 2 is the same list without its first product (the five products below 2^-8 of the result): the executor runs
+// them as one launch and the dominant (hi,hi) product as a second, plain launch whose epilogue adds the first result in fp32
+// -- the tensor core's accumulator TRUNCATES on every add, and five sixths of those truncations then happen on a sum that
+// is 2^-8 of the result (measured: 5e-6 -> 1e-6 relative error on K = 1152).
+__device__ __forceinline__ int a_chunk(int kc, int cpp, uint32_t tab) {
+    if (cpp == 0) return kc;
+    const int pr = kc / cpp;
+    return (int)((tab >> (4 * pr)) & 0xFu) * cpp + (kc - pr * cpp);
+}
 
 // trace slots (CTA 0 only): 0 entry, 1 setup done, 2 dependency wait passed, 3 first TMA issued, 4 first operand stage landed,
 // 5/6 accumulator commit of tile 0/1, 7/9 epilogue sees accumulator of tile 0/1, 8/10 epilogue of tile 0/1 done, 11 exit
@@ -277,7 +293,7 @@ __device__ __forceinline__ void epi_rows(const TcArgs& a, const CUtensorMap* tmO
                     if (j < a.nchw_valid) op[(long long)j * a.HWout] = v[j];
             } else if (a.out_f32) {
                 if (a.residual) {
-                    const float* rp = reinterpret_cast<const float*>(a.residual) + m * a.ldr + n;
+                    const float* rp = reinterpret_cast<const float*>(a.residual) + e.orow * a.ldr + n;  // orow == m unless sub-pixel
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b4 = *reinterpret_cast<const float4*>(rp + j);
@@ -651,7 +667,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             ptx::mbar_arrive(&full[s]);
                         } else {
                             ptx::mbar_arrive_expect_tx(&full[s], halo_bytes + 3 * C::kBBytes);
-                            ptx::tma_load_4d(sa, &tmA0, &full[s], kc * kBK, dx - a.pad, cy0[0] - a.pad, n_img[0]);
+                            ptx::tma_load_4d(sa, &tmA0, &full[s], a_chunk(kc, a.split_cpp, a.split_tab) * kBK, dx - a.pad, cy0[0] - a.pad, n_img[0]);
 #pragma unroll
                             for (int dy = 0; dy < 3; ++dy)
                                 ptx::tma_load_2d(sa + kHaloABytes + dy * C::kBBytes, &tmB, &full[s],
@@ -776,7 +792,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
 #pragma unroll
                             for (int h = 0; h < MT; ++h)
-                                ptx::tma_load_4d(sa + h * kABytes, tm, &full[s], kc * kBK, cx, cy0[h] + dy - pad, n_img[h]);
+                                ptx::tma_load_4d(sa + h * kABytes, tm, &full[s], a_chunk(kc, g == 0 ? a.split_cpp : 0, a.split_tab) * kBK, cx, cy0[h] + dy - pad, n_img[h]);
                             if (a.b_batched)
                                 ptx::tma_load_3d(sb, &tmB, &full[s], kb_lin * kBK, nt * BN, bb);
                             else
@@ -1050,7 +1066,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                             if (leader && first) ptx::mbar_arrive_expect_tx(fbar, nb_grp * 2 * C::kStage);  // bytes of BOTH CTAs
 #pragma unroll
                             for (int h = 0; h < MT; ++h)
-                                ptx::tma2_load_4d(sa + h * kABytes, tm, fbar, kc * kBK, cx, cy0[h] + dy - pad, n_img[h]);
+                                ptx::tma2_load_4d(sa + h * kABytes, tm, fbar, a_chunk(kc, g == 0 ? a.split_cpp : 0, a.split_tab) * kBK, cx, cy0[h] + dy - pad, n_img[h]);
                             if (a.b_batched)
                                 ptx::tma2_load_3d(sb, &tmB, fbar, kb_lin * kBK, nrow, bb);
                             else
@@ -1277,10 +1293,16 @@ int pick_mt(int m_tiles, int n_tiles, int BN, bool allow2) {
 bool gemm_tc_supported(const GemmParams& p) {
     if (p.a_dtype != DT_BF16 || p.b_dtype != DT_BF16) return false;
     if (p.out_dtype != DT_BF16 && p.out_dtype != DT_F32) return false;
+    const int kf = p.a_split3 == 1 ? 6 : (p.a_split3 == 2 ? 5 : 1);  // tc32: (A piece, B piece) products per tap
+    if (p.a_split3 < 0 || p.a_split3 > 2) return false;
+    if (p.a_split3 && (p.C1 || p.tail_1x1 || p.out_dtype != DT_F32 || p.fuse_softmax || p.b_batch_stride || p.a_shared ||
+                       p.stats_out || p.out_nchw_valid))
+        return false;
     if (p.b_layout != BL_NK || (p.ups != 0 && p.ups != 2)) return false;
     if (p.ups == 2) {
         // sub-pixel upsample-conv: B = [4 phases][N][4*C0], geometry is tiled on the SOURCE grid
-        if (p.taps != 4 || p.C1 || p.stride != 1 || p.temb || p.residual || p.b_batch_stride || p.a_shared) return false;
+        if (p.taps != 4 || p.C1 || p.stride != 1 || p.temb || p.b_batch_stride || p.a_shared) return false;
+        if (p.residual && p.out_dtype != DT_F32) return false;  // the fp32 epilogue reads the residual at the scattered output row
         if (p.Hout != 2 * p.Hin || p.Wout != 2 * p.Win || ((p.Hin * p.Win) % 32) || (p.M % (4 * kBM))) return false;
         if (pick_bn(p.N) != 256 && ((p.M / 4 / kBM) % 2)) return false;
     }
@@ -1321,7 +1343,7 @@ bool gemm_tc_supported(const GemmParams& p) {
     if (p.residual && p.out_dtype == DT_BF16 && (!wdm_aligned(p.residual, 32) || (p.ldr % 16))) return false;  // 256-bit loads
     if (p.temb && (!wdm_aligned(p.temb, 16) || (p.temb_ld % 4))) return false;
     if (p.temb && p.temb_rows > 1 && ((p.Hout * p.Wout) % 32)) return false;  // the epilogue stages one temb row per warp
-    if (!p.tail_1x1 && p.K != p.taps * (p.C0 + p.C1)) return false;
+    if (!p.tail_1x1 && p.K != p.taps * kf * (p.C0 + p.C1)) return false;
     return true;
 }
 
@@ -1389,8 +1411,9 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
                           pick_mt(m_tiles_all, p.N / BN, BN, true) == 2;
 
     CUtensorMap A0, A1, A2, B;
+    const int a_pieces = p.a_split3 ? 3 : 1;  // tc32: [hi | mid | lo] channel blocks in one tensor
     auto make_a = [&](CUtensorMap* m, const void* src, int C, int ld) -> int {
-        uint64_t dims[4] = {(uint64_t)C, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)npatch};
+        uint64_t dims[4] = {(uint64_t)C * a_pieces, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)npatch};
         uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)p.Win * ld * 2, (uint64_t)p.Hin * p.Win * ld * 2};
         uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(g.Wb * p.stride), (uint32_t)(g.Hb * p.stride), (uint32_t)g.Nb};
         uint32_t es[4] = {1, (uint32_t)p.stride, (uint32_t)p.stride, 1};
@@ -1399,7 +1422,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     };
     int r;
     if (use_halo) {
-        uint64_t dims[4] = {(uint64_t)p.C0, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)npatch};
+        uint64_t dims[4] = {(uint64_t)p.C0 * a_pieces, (uint64_t)p.Win, (uint64_t)p.Hin, (uint64_t)npatch};
         uint64_t strides[3] = {(uint64_t)p.ld0 * 2, (uint64_t)p.Win * p.ld0 * 2, (uint64_t)p.Hin * p.Win * p.ld0 * 2};
         uint32_t box[4] = {(uint32_t)kBK, (uint32_t)g.Wb, (uint32_t)(2 * g.Hb + 2), 1};
         r = make_tmap(&A0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, p.src0, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1441,7 +1464,9 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     a.n_tiles = p.N / BN;
     a.M = p.M;
     a.nseg = 1;
-    a.seg_taps[0] = p.taps, a.seg_kc[0] = p.C0 / kBK;
+    a.seg_taps[0] = p.taps, a.seg_kc[0] = (p.a_split3 == 1 ? 6 : (p.a_split3 == 2 ? 5 : 1)) * (p.C0 / kBK);
+    a.split_cpp = p.a_split3 ? p.C0 / kBK : 0;
+    a.split_tab = p.a_split3 == 2 ? 0x20110u : 0x201100u;  // A pieces (hi,) hi, mid, mid, hi, lo
     a.seg_taps[1] = a.seg_taps[2] = 1, a.seg_kc[1] = a.seg_kc[2] = 0;
     if (p.C1) a.seg_kc[1] = p.C1 / kBK, a.nseg = 2;              // 1x1 over a concat, or the first shortcut tail
     if (p.tail_1x1 && p.C2) a.seg_kc[2] = p.C2 / kBK, a.nseg = 3;  // second shortcut tail

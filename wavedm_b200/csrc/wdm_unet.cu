@@ -32,6 +32,10 @@ struct ConvSpec {
     float* pw32 = nullptr;    // fp32 copy (conv_out only)
     float* pb_pad = nullptr;  // conv_out on the tensor-core path: bias zero-padded to 64
     void* pw_subpix = nullptr;  // upsample convs, bf16 mode: [4 phases][Cout][4 taps][Cin] (sub-pixel decomposition)
+    // tc32 (fp32 mode on the tensor cores, see wdm_elem.cu): the 3-way bf16 split of the weights, dominant product apart:
+    void* pw3 = nullptr;        //   the five small products [Cout][taps][5][Cin]
+    void* pw3m = nullptr;       //   the (hi, hi) product    [Cout][taps][Cin]
+    void* pw_subpix3 = nullptr, *pw_subpix3m = nullptr;  // the same for the sub-pixel weights [4 phases][Cout][4 taps][..][Cin]
 };
 struct GnSpec {
     int C = 0, w = -1, b = -1;
@@ -322,6 +326,16 @@ int pack_model(wdm_unet* net, const float* flat, cudaStream_t s, size_t* total) 
             if (e != cudaSuccess) st = wdm_cuda_error((int)e);
         }
     };
+    // tc32: 3-way bf16 split of a packed fp32 matrix [rows][taps][C] -> [rows][taps][6][C]
+    const bool tc32 = dt == DT_F32 && (net->flags & WDM_ENGINE_TC32);
+    auto split_w = [&](void** dst, void** dst_main, const void* src_f32, int rows, int taps, int C) {
+        *dst = *dst_main = nullptr;
+        if (!tc32 || (C % 64) || (rows % 64)) return;
+        *dst = take((size_t)rows * taps * 5 * C * 2);
+        *dst_main = take((size_t)rows * taps * C * 2);
+        if (fill && st == WDM_OK)
+            st = launch_split3_weight(reinterpret_cast<const float*>(src_f32), rows, taps, C, *dst, *dst_main, s);
+    };
     auto pack_conv = [&](ConvSpec& c, int cin_pad) {
         c.Cin_pad = cin_pad;
         const long long ldk = (long long)c.taps * cin_pad;
@@ -329,6 +343,7 @@ int pack_model(wdm_unet* net, const float* flat, cudaStream_t s, size_t* total) 
         if (fill && st == WDM_OK)
             st = launch_pack_conv_weight(flat + m.params[c.w].off, c.Cout, c.Cin, c.taps, cin_pad, c.pw, dt, ldk, 0, s);
         copy_f32(c.b, &c.pb);
+        split_w(&c.pw3, &c.pw3m, c.pw, c.Cout, c.taps, cin_pad);
     };
     auto pack_gn = [&](GnSpec& g) {
         copy_f32(g.w, &g.gamma);
@@ -371,6 +386,7 @@ int pack_model(wdm_unet* net, const float* flat, cudaStream_t s, size_t* total) 
                 if (e != cudaSuccess && st == WDM_OK) st = wdm_cuda_error((int)e);
             }
         }
+        split_w(&a.qkv.pw3, &a.qkv.pw3m, a.qkv.pw, 3 * C, 1, C);
         pack_conv(a.proj, C);
         if (dt == DT_BF16) {
             a.gw = take((size_t)C * C * es);
@@ -437,6 +453,13 @@ int pack_model(wdm_unet* net, const float* flat, cudaStream_t s, size_t* total) 
                 c.pw_subpix = take((size_t)16 * c.Cout * c.Cin * es);
                 if (fill && st == WDM_OK)
                     st = launch_pack_subpix_weight(flat + m.params[c.w].off, c.Cout, c.Cin, c.pw_subpix, dt, s);
+            } else if (tc32) {
+                // the pre-summed phase weights in fp32 (scratch inside the packed arena), then their split
+                ConvSpec& c = lv.resample;
+                float* tmp = reinterpret_cast<float*>(take((size_t)16 * c.Cout * c.Cin * 4));
+                if (fill && st == WDM_OK)
+                    st = launch_pack_subpix_weight(flat + m.params[c.w].off, c.Cout, c.Cin, tmp, DT_F32, s);
+                split_w(&c.pw_subpix3, &c.pw_subpix3m, tmp, 4 * c.Cout, 4, c.Cin);
             }
         }
     }
@@ -510,10 +533,60 @@ bool will_use_tc(const Ctx& c, const GemmParams& p) {
     return c.net->dt == DT_BF16 && !(c.net->flags & WDM_ENGINE_NO_TC) && gemm_tc_supported(p);
 }
 
+int run_gemm_impl(Ctx& c, const GemmParams& p);
+
+// tc32: the fp32 contraction p on the tcgen05 kernel -- split the A operand (the channel concat of src0 / src1) into its
+// three bf16 pieces in arena scratch and contract with the pre-split weights p.B3 (six products per tap). tc32_plan returns
+// false when the shape stays on the CUDA-core kernel (conv_in's 96 channels, batched attention products, virtual
+// upsampling); q = the tensor-core problem with the A pointer still to be filled in.
+bool tc32_plan(const Ctx& c, const GemmParams& p, GemmParams* q) {
+    if (c.net->dt != DT_F32 || !(c.net->flags & WDM_ENGINE_TC32) || (c.net->flags & WDM_ENGINE_NO_TC) || !p.B3 || !p.B3m) return false;
+    if (p.b_batch_stride || p.a_shared || p.tail_1x1 || p.ups == 1 || p.out_dtype != DT_F32 || p.fuse_softmax) return false;
+    const int C = p.C0 + p.C1;
+    *q = p;
+    q->src1 = nullptr, q->C1 = 0, q->ld1 = 0;
+    q->C0 = C, q->ld0 = 3 * C;
+    q->B = p.B3, q->ldb = p.taps * 5 * C, q->K = p.taps * 5 * C;
+    q->a_dtype = q->b_dtype = DT_BF16, q->a_split3 = 2;
+    q->src0 = reinterpret_cast<void*>(16);  // alignment placeholder for the support check
+    return gemm_tc_supported(*q);
+}
+
+bool run_gemm_tc32(Ctx& c, const GemmParams& p) {
+    GemmParams q;
+    if (!tc32_plan(c, p, &q)) return false;
+    const int C = p.C0 + p.C1;
+    const long long rows = (long long)((p.M + p.Hout * p.Wout - 1) / (p.Hout * p.Wout)) * p.Hin * p.Win;
+    void* sp = c.ar->alloc((size_t)rows * 3 * C * 2);
+    float* tmp = reinterpret_cast<float*>(c.ar->alloc((size_t)p.M * p.N * sizeof(float)));
+    if (c.ar->failed) c.fail(WDM_ERR_WORKSPACE);
+    if (!c.dry() && c.st == WDM_OK) {
+        c.fail(launch_split3_act(reinterpret_cast<const float*>(p.src0), p.C0, reinterpret_cast<const float*>(p.src1), p.C1, rows, sp,
+                                 c.s));
+        // 1. the five small products (+ bias, timestep row, residual) -> tmp
+        q.src0 = sp, q.out = tmp, q.ldo = p.N;
+        if (c.st == WDM_OK) run_gemm_impl(c, q);
+        // 2. the dominant (hi, hi) product: a plain bf16 contraction over the first C channels of the split tensor, + tmp
+        GemmParams m = q;
+        m.a_split3 = 0, m.B = p.B3m, m.ldb = p.taps * C, m.K = p.taps * C;
+        m.bias = nullptr, m.temb = nullptr, m.temb_rows = 0;
+        m.residual = tmp, m.ldr = p.N, m.out = p.out, m.ldo = p.ldo;
+        if (c.st == WDM_OK) run_gemm_impl(c, m);
+    }
+    c.ar->free(tmp);
+    c.ar->free(sp);
+    return true;
+}
+
 int run_gemm(Ctx& c, const GemmParams& p) {
+    if (run_gemm_tc32(c, p)) return c.st;
+    return run_gemm_impl(c, p);
+}
+
+int run_gemm_impl(Ctx& c, const GemmParams& p) {
     if (c.dry() || c.st != WDM_OK) return c.st;
     int st;
-    const bool tc = will_use_tc(c, p);
+    const bool tc = (p.a_split3 || (c.net->dt == DT_F32 && p.a_dtype == DT_BF16)) ? true : will_use_tc(c, p);
     if (!tc && c.net->dt == DT_BF16 && !(c.net->flags & (WDM_ENGINE_NO_TC | WDM_ENGINE_ALLOW_SIMT))) {
         // bf16 mode never drops to the CUDA-core kernel silently: a shape the tcgen05 kernel does not tile is an error
         c.fail(WDM_ERR_UNSUPPORTED);
@@ -524,7 +597,8 @@ int run_gemm(Ctx& c, const GemmParams& p) {
     if (c.net->profile) {
         cudaEventCreate(&sp.a);
         cudaEventCreate(&sp.b);
-        sp.flops = 2.0 * p.M * p.N * p.K;
+        sp.flops = p.a_split3 == 2 ? 0.0 : 2.0 * p.M * p.N * p.K / (p.a_split3 ? 6 : 1);  // tc32: six products per algorithmic MAC,
+                                                                                           // counted on the (hi, hi) launch
         sp.tc = tc;
         sp.M = p.M, sp.N = p.N, sp.K = p.K, sp.taps = p.taps, sp.W = p.Wout;
         sp.tag = (p.tail_1x1 ? 1 : 0) | (p.ups == 2 ? 2 : 0) | (p.fuse_softmax ? 4 : 0) | (p.b_batch_stride ? 8 : 0) |
@@ -564,7 +638,7 @@ Act conv_op(Ctx& c, const Act& a, const Act* a2, const ConvSpec& w, int stride, 
     if (a2) p.src1 = a2->p, p.C1 = a2->C, p.ld1 = a2->C;
     p.Hin = a.H, p.Win = a.W, p.Hout = Hout, p.Wout = Wout;
     p.taps = w.taps, p.stride = stride, p.pad = (w.taps == 9 && stride == 1) ? 1 : 0, p.ups = ups;
-    p.B = w.pw, p.ldb = w.taps * w.Cin_pad, p.b_layout = BL_NK;
+    p.B = w.pw, p.B3 = w.pw3, p.B3m = w.pw3m, p.ldb = w.taps * w.Cin_pad, p.b_layout = BL_NK;
     p.M = c.P * Hout * Wout, p.N = w.Cout, p.K = w.taps * (p.C0 + p.C1);
     p.alpha = 1.f, p.bias = w.pb;
     if (temb_row) p.temb = temb_row, p.temb_rows = c.T, p.temb_ld = c.net->model.temb_total;
@@ -619,13 +693,14 @@ Act gn_op(Ctx& c, const Act& a, const Act* a2, const GnSpec& g, int silu) {
 // grid (2.25x fewer FLOPs, no materialised 4x tensor). Returns an empty Act (C == 0) when the shape is not supported.
 Act upsample_conv_subpix(Ctx& c, const Act& a, const ConvSpec& w) {
     Act none;
-    if (!w.pw_subpix) return none;
+    const bool t32 = c.net->dt == DT_F32 && w.pw_subpix3;  // tc32: the same decomposition with split operands
+    if (!w.pw_subpix && !t32) return none;
     GemmParams p;
     memset(&p, 0, sizeof p);
     p.src0 = a.p, p.C0 = a.C, p.ld0 = a.C;
     p.Hin = a.H, p.Win = a.W, p.Hout = 2 * a.H, p.Wout = 2 * a.W;
     p.taps = 4, p.stride = 1, p.pad = 0, p.ups = 2;
-    p.B = w.pw_subpix, p.ldb = 4 * w.Cin, p.b_layout = BL_NK;
+    p.B = w.pw_subpix, p.B3 = w.pw_subpix3, p.B3m = w.pw_subpix3m, p.ldb = 4 * w.Cin, p.b_layout = BL_NK;
     // phase-major m-tiles of 128 source pixels: a source grid of 64 pixels pairs two patches per tile -> even count (see Ctx::Pa)
     const int Prun = (a.H * a.W < 128) ? c.Pa : c.P;
     p.M = Prun * p.Hout * p.Wout, p.N = w.Cout, p.K = 4 * a.C;
@@ -633,6 +708,14 @@ Act upsample_conv_subpix(Ctx& c, const Act& a, const ConvSpec& w) {
     p.ldo = w.Cout;
     p.a_dtype = p.b_dtype = p.out_dtype = c.net->dt;
     p.out = reinterpret_cast<void*>(16);  // placeholder for the support check (alignment only)
+    if (t32) {
+        GemmParams q;
+        if (!tc32_plan(c, p, &q)) return none;
+        Act o = new_act(c, p.Hout, p.Wout, w.Cout);
+        p.out = o.p;
+        run_gemm(c, p);
+        return o;
+    }
     if (!will_use_tc(c, p)) return none;
     Act o = new_act(c, p.Hout, p.Wout, w.Cout);
     p.out = o.p;
@@ -902,10 +985,10 @@ int forward_impl(wdm_unet* net, Arena* ar, const void* x, const float* t, int T,
         }
         if (m.up[lv].has_resample) {
             Act h2;
-            if (fold_ups) {
+            if (Act sp = upsample_conv_subpix(c, h, m.up[lv].resample); sp.p || (c.dry() && sp.C)) {
+                h2 = sp;  // bf16 tensor-core mode, or fp32 with WDM_ENGINE_TC32
+            } else if (fold_ups) {
                 h2 = conv_op(c, h, nullptr, m.up[lv].resample, 1, 1, nullptr, nullptr, true);
-            } else if (Act sp = upsample_conv_subpix(c, h, m.up[lv].resample); sp.p || (c.dry() && sp.C)) {
-                h2 = sp;
             } else {
                 Act u = new_act(c, h.H * 2, h.W * 2, h.C);
                 if (!c.dry() && c.st == WDM_OK) c.fail(launch_upsample2x(h.p, net->dt, P, h.H, h.W, h.C, u.p, s));
@@ -994,6 +1077,7 @@ extern "C" size_t wdm_unet_packed_bytes(const wdm_unet_config* cfg, int precisio
     wdm_unet net;
     if (build_model(*cfg, &net.model) != WDM_OK) return 0;
     net.dt = precision == WDM_PREC_FP32 ? DT_F32 : DT_BF16;
+    net.flags = precision == WDM_PREC_FP32 ? WDM_ENGINE_TC32 : 0;  // upper bound over the engine flags: tc32 adds the split weights
     size_t total = 0;
     pack_model(&net, nullptr, 0, &total);
     return total;
@@ -1025,6 +1109,7 @@ extern "C" int wdm_unet_create(const wdm_unet_config* cfg, int precision, int fl
         wdm_unet probe;
         probe.model = net->model;
         probe.dt = net->dt;
+        probe.flags = flags;
         pack_model(&probe, nullptr, 0, &need);
     }
     if (packed_bytes < need) {
@@ -1185,4 +1270,12 @@ extern "C" int wdm_softmax_rows(const float* S, int rows, int L, void* out, int 
     if (!S || !out) return WDM_ERR_BAD_ARG;
     return launch_softmax_rows(S, rows, L, out, out_dtype == WDM_PREC_FP32 ? DT_F32 : DT_BF16,
                                static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int wdm_split3_act(const float* src0, int C0, const float* src1, int C1, long long rows, void* out, void* stream) {
+    return launch_split3_act(src0, C0, src1, C1, rows, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int wdm_split3_weight(const float* w, int N, int taps, int C, void* out, void* out_main, void* stream) {
+    return launch_split3_weight(w, N, taps, C, out, out_main, static_cast<cudaStream_t>(stream));
 }

@@ -8,13 +8,17 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib
 
-PREC = {"fp32": _lib.WDM_PREC_FP32, "bf16": _lib.WDM_PREC_BF16}
+#: "fp32"      parity mode: fp32 storage, contractions on the tcgen05 kernel through the 3-way bf16 operand split (tc32)
+#: "fp32_ffma" the same with every contraction on the CUDA-core FFMA kernel (round-to-nearest accumulation: tightest parity)
+#: "bf16"      throughput mode: bf16 storage, tcgen05 contractions
+PREC = {"fp32": _lib.WDM_PREC_FP32, "fp32_ffma": _lib.WDM_PREC_FP32, "bf16": _lib.WDM_PREC_BF16}
 
 
 class WdmUnetConfig(ctypes.Structure):
@@ -87,9 +91,17 @@ class UNetEngine:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("wavedm_b200.UNetEngine needs a CUDA device (no CPU fallback)")
+        # fp32 (parity mode): contractions on the tcgen05 kernel through the 3-way bf16 operand split (WDM_ENGINE_TC32, fp32
+        # accumulation in TMEM; storage / GroupNorm / softmax stay fp32). WDM_TC32=0 or flags |= WDM_ENGINE_NO_TC keeps every
+        # contraction on the CUDA-core FFMA kernel (the round-1 parity mode).
+        if precision == "fp32_ffma":
+            flags |= _lib.WDM_ENGINE_NO_TC
+        if precision == "fp32" and os.environ.get("WDM_TC32", "1") != "0" and not (flags & _lib.WDM_ENGINE_NO_TC):
+            flags |= _lib.WDM_ENGINE_TC32
+        self.flags = flags
         self.precision = precision
         self.prec = PREC[precision]
-        self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.cstruct = make_config_struct(config)
         self.R = int(config.data.image_size)
         # wavelet_in_unet (models/unet.py:203-206): the module consumes pixel-domain [P, 6, 4R, 4R] and returns [P, 3, 4R, 4R]

@@ -34,7 +34,7 @@ class HfrmEngine:
         if len(enc_blk_nums) != len(dec_blk_nums):
             raise ValueError("enc_blk_nums and dec_blk_nums must have the same length (arch.py:218-230)")
         self.precision = precision
-        self.prec = {"fp32": _lib.WDM_PREC_FP32, "bf16": _lib.WDM_PREC_BF16}[precision]
+        self.prec = {"fp32": _lib.WDM_PREC_FP32, "fp32_ffma": _lib.WDM_PREC_FP32, "bf16": _lib.WDM_PREC_BF16}[precision]
         cfg = _HfrmConfig()
         cfg.in_channel, cfg.dim, cfg.mid_blk_num, cfg.n_levels = in_channel, dim, mid_blk_num, len(enc_blk_nums)
         for i, (a, b) in enumerate(zip(enc_blk_nums, dec_blk_nums)):
