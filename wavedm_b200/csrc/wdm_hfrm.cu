@@ -639,7 +639,9 @@ struct StripCfg {
     static int smem_bytes(int N) { return ((N * kLd * 2 + 2 * N * 4 + 127) / 128) * 128 + 8 * kWarpBytes; }
 };
 
-template <int K>
+// PRO / EPI are template parameters: the four combinations a ResidualBlock uses compile to straight-line code (the runtime
+// switches of the generic kernels cost this one a third of its issue slots)
+template <int K, int PRO, int EPI>
 __global__ void __launch_bounds__(256) hfrm_pw_strip_kernel(const PwParams p, long long n_strips) {
     using C = StripCfg<K>;
     constexpr int LD = C::kLd, VPR = K / 8, NV = 16 * VPR / 32, RPS = 32 / VPR;  // vectors / row, vectors / lane, rows / slot
@@ -682,12 +684,12 @@ __global__ void __launch_bounds__(256) hfrm_pw_strip_kernel(const PwParams p, lo
         }
         for (int i = tid; i < p.N; i += 256) {
             bias_s[i] = p.bias ? p.bias[i] : 0.f;
-            wsum_s[i] = (p.pro == PRO_LN && p.wsum) ? p.wsum[i] : 0.f;
+            wsum_s[i] = (PRO == PRO_LN && p.wsum) ? p.wsum[i] : 0.f;
         }
     }
     __syncthreads();
 
-    const bool gate = p.epi == EPI_GATE;
+    constexpr bool gate = EPI == EPI_GATE;
     const int g = lane >> 2, s = lane & 3;
     const int ngroups = (p.N + 63) / 64;
     bf16* out = reinterpret_cast<bf16*>(p.out);
@@ -698,13 +700,13 @@ __global__ void __launch_bounds__(256) hfrm_pw_strip_kernel(const PwParams p, lo
         cp_async_wait<kStripStages - 2>();
         // ---- row statistics / channel-attention scale on the vectors this lane copied
         float mean[NV], rstd[NV];
-        if (p.pro != PRO_NONE) {
+        if (PRO != PRO_NONE) {
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 const int vec = lane + 32 * i, r = vec / VPR, kv = (vec - r * VPR) * 8;
                 float v[8];
                 load8(st + r * LD + kv, v);
-                if (p.pro == PRO_LN) {
+                if (PRO == PRO_LN) {
                     float a = 0.f, b = 0.f;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) a += v[q], b = fmaf(v[q], v[q], b);
@@ -725,7 +727,7 @@ __global__ void __launch_bounds__(256) hfrm_pw_strip_kernel(const PwParams p, lo
         // statistics of the rows whose accumulators this lane holds: g and g + 8. Row r sits in slot r / RPS of the lanes
         // (r % RPS) * VPR ..; with VPR == 4 that is this lane's own group
         float mu0 = 0.f, rs0 = 1.f, mu1 = 0.f, rs1 = 1.f;
-        if (p.pro == PRO_LN) {
+        if (PRO == PRO_LN) {
             if (VPR == 4) {
                 mu0 = mean[0], rs0 = rstd[0], mu1 = mean[NV - 1], rs1 = rstd[NV - 1];
             } else {
@@ -777,7 +779,7 @@ __global__ void __launch_bounds__(256) hfrm_pw_strip_kernel(const PwParams p, lo
                     const int row = g + 8 * hr;
                     float f0 = acc[(np * 2) * 4 + 2 * hr], f1 = acc[(np * 2) * 4 + 2 * hr + 1];
                     float g0 = acc[(np * 2 + 1) * 4 + 2 * hr], g1 = acc[(np * 2 + 1) * 4 + 2 * hr + 1];
-                    if (p.pro == PRO_LN) {
+                    if (PRO == PRO_LN) {
                         const float mu = hr ? mu1 : mu0, rs = hr ? rs1 : rs0;
                         f0 = rs * (f0 - mu * wf.x), f1 = rs * (f1 - mu * wf.y);
                         g0 = rs * (g0 - mu * wg.x), g1 = rs * (g1 - mu * wg.y);
@@ -793,9 +795,9 @@ __global__ void __launch_bounds__(256) hfrm_pw_strip_kernel(const PwParams p, lo
             }
             __syncwarp();
             // ---- coalesced 16-byte stores (+ residual, loaded first)
-            const int tno = gate ? 32 : 64, vpr = tno / 8;
+            constexpr int tno = gate ? 32 : 64, vpr = tno / 8;
             const int nout = gate ? p.N / 2 : p.N, nbase = gate ? n0 / 2 : n0;
-            const int nit = 16 * vpr / 32;  // 4 (2 with the gate)
+            constexpr int nit = 16 * vpr / 32;  // 4 (2 with the gate)
             long long om[4];
             int oc[4], pr[4], pc[4];
             uint4 rv[4];
@@ -806,14 +808,14 @@ __global__ void __launch_bounds__(256) hfrm_pw_strip_kernel(const PwParams p, lo
                 const int idx = lane + 32 * it, row = idx / vpr, cv = (idx - row * vpr) * 8;
                 if (m0 + row >= p.M || nbase + cv >= nout) continue;
                 om[it] = m0 + row, oc[it] = nbase + cv, pr[it] = row, pc[it] = cv;
-                if (p.epi == EPI_RES) rv[it] = *reinterpret_cast<const uint4*>(res + om[it] * p.ldr + oc[it]);
+                if (EPI == EPI_RES) rv[it] = *reinterpret_cast<const uint4*>(res + om[it] * p.ldr + oc[it]);
             }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 if (om[it] < 0) continue;
                 float v[8];
                 load8(patch + pr[it] * kStripPatchLd + pc[it], v);
-                if (p.epi == EPI_RES) {
+                if (EPI == EPI_RES) {
                     const uint32_t w4[4] = {rv[it].x, rv[it].y, rv[it].z, rv[it].w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -829,23 +831,35 @@ __global__ void __launch_bounds__(256) hfrm_pw_strip_kernel(const PwParams p, lo
     cp_async_wait<0>();
 }
 
-template <int K>
-int launch_pw_strip(const PwParams& p, cudaStream_t s, int sms) {
+template <int K, int PRO, int EPI>
+int launch_pw_strip_t(const PwParams& p, cudaStream_t s, int sms) {
     using C = StripCfg<K>;
     const int smem = C::smem_bytes(p.N);
-    static bool attr[2] = {false, false};
-    if (!attr[K == 64]) {
-        cudaError_t e = cudaFuncSetAttribute(hfrm_pw_strip_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(hfrm_pw_strip_kernel<K, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::smem_bytes(128));
         if (e != cudaSuccess) return wdm_cuda_error((int)e);
-        attr[K == 64] = true;
+        attr = true;
     }
     const long long n_strips = ((long long)p.M + 15) / 16;
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;
     const long long want = (n_strips + 7) / 8;
     const int grid = (int)(want < (long long)per_sm * sms ? want : (long long)per_sm * sms);
-    hfrm_pw_strip_kernel<K><<<grid, 256, smem, s>>>(p, n_strips);
+    hfrm_pw_strip_kernel<K, PRO, EPI><<<grid, 256, smem, s>>>(p, n_strips);
     return wdm_launch_status();
+}
+
+// the (prologue, epilogue) pairs of a ResidualBlock; anything else goes to the ring kernel
+template <int K>
+int launch_pw_strip(const PwParams& p, cudaStream_t s, int sms, bool* handled) {
+    *handled = true;
+    if (p.pro == PRO_LN && p.epi == EPI_BIAS) return launch_pw_strip_t<K, PRO_LN, EPI_BIAS>(p, s, sms);
+    if (p.pro == PRO_LN && p.epi == EPI_GATE) return launch_pw_strip_t<K, PRO_LN, EPI_GATE>(p, s, sms);
+    if (p.pro == PRO_SCALE && p.epi == EPI_RES) return launch_pw_strip_t<K, PRO_SCALE, EPI_RES>(p, s, sms);
+    if (p.pro == PRO_NONE && p.epi == EPI_RES) return launch_pw_strip_t<K, PRO_NONE, EPI_RES>(p, s, sms);
+    *handled = false;
+    return WDM_OK;
 }
 
 int g_pw_ring = -1;  // WDM_HFRM_RING=0 keeps the generic kernel in bf16 mode (A/B testing)
@@ -873,8 +887,11 @@ int launch_pw(const PwParams& p, cudaStream_t s) {
                 if (e != cudaSuccess) return wdm_cuda_error((int)e);
             }
             // C = 32 / 64 (full / half resolution, HBM bound): resident weights, one pipeline per warp
-            if (g_pw_ring != 2 && (p.K == 32 || p.K == 64) && p.N <= 128 && p.a_mode == AM_PLAIN && p.epi != EPI_SHUFFLE)
-                return p.K == 32 ? launch_pw_strip<32>(p, s, sms) : launch_pw_strip<64>(p, s, sms);
+            if (g_pw_ring != 2 && (p.K == 32 || p.K == 64) && p.N <= 128 && p.a_mode == AM_PLAIN && p.epi != EPI_SHUFFLE) {
+                bool handled = false;
+                const int r = p.K == 32 ? launch_pw_strip<32>(p, s, sms, &handled) : launch_pw_strip<64>(p, s, sms, &handled);
+                if (handled) return r;
+            }
             const long long total = (long long)m_tiles * n_tiles;
             const int grid = (int)(total < 2LL * sms ? total : 2LL * sms);
             hfrm_pw_ring_kernel<<<grid, kPwThreads, kRingSmem, s>>>(p, m_tiles, n_tiles);
@@ -943,6 +960,19 @@ __global__ void __launch_bounds__(256, 2) hfrm_dw_gate_kernel(const T* __restric
         w[t][0] = a.x, w[t][1] = a.y, w[t][2] = d.x, w[t][3] = d.y;
     }
     b4[0] = bias[c], b4[1] = bias[c + 1], b4[2] = bias[C + c], b4[3] = bias[C + c + 1];
+    {
+        // fold the column validity of x - 1, x, x + 1 (and of the whole thread, x >= W) into the weights
+        const int xg = (blockIdx.x % tiles_x) * TW + xl;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const int xx = xg + dx - 1;
+            const float mk = (xx >= 0 && xx < W && xg < W) ? 1.f : 0.f;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) w[dy * 3 + dx][e] *= mk;
+        }
+    }
     float acc[3][4];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -952,14 +982,12 @@ __global__ void __launch_bounds__(256, 2) hfrm_dw_gate_kernel(const T* __restric
     const T* base = in + img * H * W * 2 * C;
     T* obase = out + img * H * W * C;
     const int r_last = ty0 + kDwTH < H ? ty0 + kDwTH : H;  // last input row needed (row H is the zero padding row)
-    // column validity / clamped offsets of x - 1, x, x + 1
+    // clamped offsets of x - 1, x, x + 1
     long long xoff[3];
-    float xm[3];
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
         const int xx = x + dx - 1, xc = xx < 0 ? 0 : (xx >= W ? W - 1 : xx);
         xoff[dx] = (long long)xc * 2 * C + c;
-        xm[dx] = (xx == xc && active) ? 1.f : 0.f;
     }
     // raw loads of input row r (clamped address; the mask is applied when the row is consumed): issued TWO rows ahead of
     // their use so that 18 loads per thread are in flight -- the kernel is DRAM-latency bound otherwise
@@ -976,14 +1004,9 @@ __global__ void __launch_bounds__(256, 2) hfrm_dw_gate_kernel(const T* __restric
     auto step = [&](int r, float (&v)[3][4], auto ph) {
         constexpr int PH = decltype(ph)::value;
         if (r > r_last) return;
-        const float rm = (r >= 0 && r < H) ? 1.f : 0.f;
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const float mk = rm * xm[dx];  // out-of-image neighbours: the clamped pixel with weight 0
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[dx][e] *= mk;
-        }
-        dw_accumulate<PH>(acc, v, w);
+        // rows above / below the image contribute nothing (r is uniform over the CTA: no divergence); out-of-image COLUMNS
+        // read the clamped pixel against weights that were zeroed once, above
+        if (r >= 0 && r < H) dw_accumulate<PH>(acc, v, w);
         // output row r - 1 has now seen its three input rows
         constexpr int DONE = (PH + 2) % 3;
         const int ro = r - 1;
