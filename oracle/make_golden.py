@@ -66,6 +66,34 @@ def wiu_cfg():
                             model__use_other_channels=False, model__in_channels=93, model__out_ch=48)
 
 
+def win_cfg():
+    """data.use_window: True (models/unet.py:309-336,347-348,391-392) needs in_channels + pred_channels = 6 p^2 and
+    out_ch = 3 p^2 ("needs its own config"); p = 2, 16x16 tiles of a 32x32 input."""
+    return O.default_config(data__image_size=16, data__use_window=True, data__window_size=2, model__ch=128,
+                            model__ch_mult=[1, 2], model__num_res_blocks=1, model__attn_resolutions=[8],
+                            model__use_other_channels=False, model__in_channels=21, model__out_ch=12)
+
+
+def golden_window(ref_unet):
+    """The use_window variant of the reference module on a seeded input -> unet_win.npz"""
+    cfg = win_cfg()
+    torch.manual_seed(61)
+    net = ref_unet.DiffusionUNet(cfg).eval()
+    sd_ref = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd = O.init_state_dict(cfg, seed=61)
+    assert sorted(sd.keys()) == sorted(sd_ref.keys()) and all(torch.equal(sd[k], sd_ref[k]) for k in sd)
+    g = torch.Generator().manual_seed(67)
+    xin = torch.randn(3, 6, 32, 32, generator=g)
+    t = torch.tensor([12.0, 700.0, 333.0])
+    with torch.no_grad():
+        ref_out = net(xin, t)
+        ora_out = O.unet_forward(sd, cfg, xin, t)
+    assert ref_out.shape == (3, 3, 32, 32)
+    assert torch.equal(ref_out, ora_out), float((ref_out - ora_out).abs().max())
+    np.savez(os.path.join(OUT, "unet_win.npz"), x=xin.numpy(), t=t.numpy(), out=ref_out.numpy(), seed=61, nkeys=len(sd_ref))
+    print("unet_win.npz ok; keys", len(sd_ref), "out range", float(ref_out.min()), float(ref_out.max()))
+
+
 def golden_wavelet_in_unet(ref_unet, ref_ddm):
     """models/unet.py:203-206,338-350,393-394 + the pixel-domain sampler (restoration.py:171-172) -> unet_wiu.npz"""
     cfg = wiu_cfg()
@@ -183,6 +211,9 @@ def main():
     ref_unet, ref_wavelet, ref_ddm, ref_sampling, ref_metrics = import_reference()
     if "--only-wiu" in sys.argv:   # regenerate just the wavelet_in_unet vectors
         golden_wavelet_in_unet(ref_unet, ref_ddm)
+        return
+    if "--only-win" in sys.argv:
+        golden_window(ref_unet)
         return
     if "--only-hfrm" in sys.argv:
         golden_hfrm()
@@ -330,6 +361,7 @@ def main():
     print("sandwich_full.npz ok; psnr", float(psnr), "latent range", float(lat.min()), float(lat.max()))
     golden_wavelet_in_unet(ref_unet, ref_ddm)
     golden_hfrm()
+    golden_window(ref_unet)
     golden_sandwich_s50(ref_unet, ref_wavelet, ref_ddm, ref_metrics)
 
 

@@ -148,6 +148,20 @@ def iwt_torch(y: Tensor) -> Tensor:
     return F.conv_transpose2d(xx, haar_conv_weight(), stride=4, groups=3)
 
 
+def to_win(x: Tensor, p: int) -> Tensor:
+    """models/unet.py:309-314."""
+    B, C, H, W = x.shape
+    x = x.view(B, C, p, H // p, p, W // p).permute(0, 1, 2, 4, 3, 5).contiguous()
+    return x.view(B, -1, H // p, W // p)
+
+
+def win_back(x: Tensor, p: int) -> Tensor:
+    """models/unet.py:316-321."""
+    B, C, H, W = x.shape
+    x = x.view(B, C // (p ** 2), p, p, H, W).permute(0, 1, 2, 4, 3, 5).contiguous()
+    return x.view(B, C // (p ** 2), H * p, W * p)
+
+
 def unet_forward(sd: Dict[str, Tensor], cfg, x: Tensor, t: Tensor) -> Tensor:
     """models/unet.py:346-395 with use_window=False (identical network to models/unet_wav.py:115-155).
     data.wavelet_in_unet: the DWT of each 3-channel half on the way in (:338-344,349-350), the IWT on the way
@@ -157,6 +171,9 @@ def unet_forward(sd: Dict[str, Tensor], cfg, x: Tensor, t: Tensor) -> Tensor:
     nres = len(ch_mult)
     res = cfg.data.image_size
     wiu = bool(getattr(cfg.data, "wavelet_in_unet", False))
+    win = bool(getattr(cfg.data, "use_window", False))
+    if win:  # models/unet.py:323-331,347-348: each 3-channel half cut into p x p tiles that become channels
+        x = torch.cat([to_win(x[:, :3], cfg.data.window_size), to_win(x[:, 3:], cfg.data.window_size)], dim=1)
     if wiu:
         x = torch.cat([dwt_torch(x[:, :3]), dwt_torch(x[:, 3:])], dim=1)
     assert x.shape[2] == x.shape[3] == res
@@ -189,6 +206,8 @@ def unet_forward(sd: Dict[str, Tensor], cfg, x: Tensor, t: Tensor) -> Tensor:
             cur *= 2
     h = swish(group_norm(h, sd, "norm_out"))
     h = conv(h, sd, "conv_out", padding=1)
+    if win:  # models/unet.py:333-336,391-392
+        h = win_back(h, cfg.data.window_size)
     return iwt_torch(h) if wiu else h
 
 

@@ -196,3 +196,18 @@ def test_hfrm_oracle_vs_reference_golden():
     y = HO.hfrm_forward(sd, torch.from_numpy(g["x"]))
     ref = torch.from_numpy(g["y"])
     assert (y - ref).abs().max() <= 2e-5 * ref.abs().max()
+
+
+def test_use_window_oracle_vs_reference_golden():
+    """data.use_window (models/unet.py:309-336,347-348,391-392): the oracle's re-layout + network against the output of the
+    reference module built with the same config (tests/golden/unet_win.npz, oracle/make_golden.py --only-win)."""
+    g = golden("unet_win.npz")
+    cfg = O.default_config(data__image_size=16, data__use_window=True, data__window_size=2, model__ch=128,
+                           model__ch_mult=[1, 2], model__num_res_blocks=1, model__attn_resolutions=[8],
+                           model__use_other_channels=False, model__in_channels=21, model__out_ch=12)
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    assert len(sd) == int(g["nkeys"])
+    with torch.no_grad():
+        out = O.unet_forward(sd, cfg, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]))
+    ref = torch.from_numpy(g["out"])
+    assert (out - ref).abs().max() <= 2e-5 * ref.abs().max()

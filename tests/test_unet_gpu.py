@@ -757,3 +757,29 @@ def test_unet_fp32_engine_uses_tensor_cores_and_matches_ffma_engine():
     rel = float((y - yf).abs().max()) / float(yf.abs().max())
     print(f"fp32 engine: tc32 vs FFMA max rel diff {rel:.2e}; launches tc {tc} simt {simt}")
     assert rel <= 2e-5
+
+
+def test_unet_use_window_module_vs_reference_golden():
+    """data.use_window through the public module (DiffusionUNet.forward): tile-major space-to-depth around the engine, conv_out
+    with 3 p^2 = 12 channels; fp32 (tc32) and bf16 engines against the reference module's output."""
+    from wavedm_b200.unet import DiffusionUNet
+    g = golden("unet_win.npz")
+    cfg = O.default_config(data__image_size=16, data__use_window=True, data__window_size=2, model__ch=128,
+                           model__ch_mult=[1, 2], model__num_res_blocks=1, model__attn_resolutions=[8],
+                           model__use_other_channels=False, model__in_channels=21, model__out_ch=12)
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    net = DiffusionUNet(cfg).eval()
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV).requires_grad_(False)
+    x, t = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["t"]).to(DEV)
+    ref = torch.from_numpy(g["out"])
+    with torch.no_grad():
+        net.engine_precision = "fp32"
+        y32 = net(x, t).cpu()
+        net.engine_precision = "bf16"
+        y16 = net(x, t).cpu()
+    assert y32.shape == ref.shape == (3, 3, 32, 32)
+    e32 = float((y32 - ref).abs().max() / ref.abs().max())
+    e16 = float((y16 - ref).norm() / ref.norm())
+    print(f"use_window: fp32 max rel {e32:.2e}, bf16 rel L2 {e16:.2e}")
+    assert e32 <= 5e-5 and e16 <= 3e-2

@@ -960,4 +960,23 @@ int launch_split3_weight(const float* w, int N, int taps, int C, void* out, void
     return wdm_launch_status();
 }
 
+__global__ void __launch_bounds__(256) rows_to_nchw_kernel(const float* __restrict__ y, int ld, long long total, int HW, int C,
+                                                          float* __restrict__ x) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // output index (p, c, pix)
+    if (i >= total) return;
+    const int pix = (int)(i % HW);
+    const long long pc = i / HW;
+    const int c = (int)(pc % C);
+    const long long pp = pc / C;
+    x[i] = y[(pp * HW + pix) * ld + c];
+}
+
+int launch_rows_to_nchw(const float* y, int ld, int P, int HW, int C, float* x, cudaStream_t s) {
+    if (!y || !x || C <= 0 || C > ld) return WDM_ERR_BAD_SHAPE;
+    const long long total = (long long)P * C * HW;
+    if (total <= 0) return WDM_OK;
+    rows_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(y, ld, total, HW, C, x);
+    return wdm_launch_status();
+}
+
 }  // namespace wdm

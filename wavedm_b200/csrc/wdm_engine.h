@@ -87,6 +87,8 @@ int launch_gather_patches(const GatherParams& p, cudaStream_t stream);
 int launch_dwt_gather(const float* src0, const float* src1, int nsrc, int B, int H, int W, const int* patches, int P, int R,
                       int Cpad, void* out, int out_dtype, cudaStream_t stream);
 int launch_iwt_nhwc(const float* y, int ld, int P, int R, float* x, cudaStream_t stream);
+// the first C columns of a row-major fp32 matrix [P*HW][ld] -> NCHW [P][C][HW] (conv_out with more than 4 channels: use_window)
+int launch_rows_to_nchw(const float* y, int ld, int P, int HW, int C, float* x, cudaStream_t stream);
 
 // Fused overlap-average + DDIM update (models/ddm_wavelet.py:485-503, eta = 0), per image pixel:
 //   et = sum_{patches covering the pixel} eps_patch / count ; x0 = (xt - et*sqrt(1-at))/sqrt(at)

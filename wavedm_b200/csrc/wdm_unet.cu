@@ -143,7 +143,8 @@ int build_model(const wdm_unet_config& cfg, Model* m) {
         cfg.n_attn_res < 0 || cfg.n_attn_res > 8 || cfg.in_channels < 1 || cfg.out_ch < 1)
         return WDM_ERR_BAD_ARG;
     // wavelet_in_unet: the DWT of the two 3-channel halves feeds the network, the IWT consumes 48 output channels
-    if (cfg.wavelet_in_unet ? (cfg.out_ch != 48 || cfg.in_channels != 96) : cfg.out_ch > 4) return WDM_ERR_BAD_ARG;
+    // out_ch <= 4: the reference configs; up to 64: data.use_window (out_ch = 3 * window_size^2), conv_out through the GEMM path
+    if (cfg.wavelet_in_unet ? (cfg.out_ch != 48 || cfg.in_channels != 96) : cfg.out_ch > 64) return WDM_ERR_BAD_ARG;
     if (cfg.resolution < (1 << (cfg.n_levels - 1)) * 2 || (cfg.resolution % (1 << (cfg.n_levels - 1))))
         return WDM_ERR_BAD_SHAPE;
     for (int i = 0; i < cfg.n_levels; ++i)
@@ -468,10 +469,20 @@ int pack_model(wdm_unet* net, const float* flat, cudaStream_t s, size_t* total) 
     {
         ConvSpec& c = m.conv_out;
         c.Cin_pad = c.Cin;
-        c.pw32 = reinterpret_cast<float*>(take((size_t)c.Cout * 9 * c.Cin * 4));
+        // rows (and bias) zero-padded to a multiple of 8: the CUDA-core GEMM tiles N in eights (Cout > 4: data.use_window)
+        const int cout8 = (c.Cout + 7) / 8 * 8;
+        c.pw32 = reinterpret_cast<float*>(take((size_t)cout8 * 9 * c.Cin * 4));
+        float* pb8 = reinterpret_cast<float*>(take((size_t)cout8 * 4));
+        if (fill && st == WDM_OK) {
+            cudaError_t e = cudaMemsetAsync(c.pw32, 0, (size_t)cout8 * 9 * c.Cin * 4, s);
+            if (e == cudaSuccess) e = cudaMemsetAsync(pb8, 0, (size_t)cout8 * 4, s);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(pb8, flat + m.params[c.b].off, (size_t)c.Cout * 4, cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) st = wdm_cuda_error((int)e);
+        }
         if (fill && st == WDM_OK)
             st = launch_pack_conv_weight(flat + m.params[c.w].off, c.Cout, c.Cin, 9, c.Cin, c.pw32, DT_F32, 9LL * c.Cin, 0, s);
-        copy_f32(c.b, &c.pb);
+        c.pb = pb8;
         if (dt == DT_BF16 && c.Cout <= 64 && (c.Cin % 64) == 0) {
             // tensor-core conv_out: Cout zero-padded to one 64-wide N tile
             c.pw = take((size_t)64 * 9 * c.Cin * es);
@@ -1002,10 +1013,10 @@ int forward_impl(wdm_unet* net, Arena* ar, const void* x, const float* t, int T,
     Act n = gn_op(c, h, nullptr, m.norm_out, 1);
     free_act(c, h);
     bool out_done = false;
-    if (m.cfg.wavelet_in_unet) {
+    if (m.cfg.wavelet_in_unet || m.conv_out.Cout > 4) {
         // conv_out -> [P*R*R][ld] fp32 (NHWC rows, 48 valid columns) -> IWT -> eps_out [P, 3, 4R, 4R]  (unet.py:393-394)
         const bool tc_out = net->dt == DT_BF16 && m.conv_out.pw && m.conv_out.pb_pad;  // bf16: Cout zero-padded to 64
-        const int ld = tc_out ? 64 : m.conv_out.Cout;
+        const int ld = tc_out ? 64 : (m.conv_out.Cout + 7) / 8 * 8;
         float* tmp = reinterpret_cast<float*>(ar->alloc((size_t)P * R * R * ld * sizeof(float)));
         if (ar->failed) c.fail(WDM_ERR_WORKSPACE);
         GemmParams p;
@@ -1018,10 +1029,12 @@ int forward_impl(wdm_unet* net, Arena* ar, const void* x, const float* t, int T,
         if (tc_out) {
             p.B = m.conv_out.pw, p.N = 64, p.bias = m.conv_out.pb_pad, p.a_dtype = p.b_dtype = DT_BF16;
         } else {
-            p.B = m.conv_out.pw32, p.N = m.conv_out.Cout, p.bias = m.conv_out.pb, p.a_dtype = net->dt, p.b_dtype = DT_F32;
+            p.B = m.conv_out.pw32, p.N = ld, p.bias = m.conv_out.pb, p.a_dtype = net->dt, p.b_dtype = DT_F32;
         }
         run_gemm(c, p);
-        if (!c.dry() && c.st == WDM_OK) c.fail(launch_iwt_nhwc(tmp, ld, P, R, eps_out, s));
+        if (!c.dry() && c.st == WDM_OK)
+            c.fail(m.cfg.wavelet_in_unet ? launch_iwt_nhwc(tmp, ld, P, R, eps_out, s)
+                                         : launch_rows_to_nchw(tmp, ld, P, R * R, m.conv_out.Cout, eps_out, s));
         ar->free(tmp);
         out_done = true;
     }

@@ -81,8 +81,7 @@ def temb_freqs(ch: int) -> torch.Tensor:
 class UNetEngine:
     def __init__(self, config, state_dict: Dict[str, torch.Tensor], device, precision: str = "bf16", flags: int = 0,
                  max_patches: int = 64):
-        if getattr(config.data, "use_window", False):
-            raise NotImplementedError("the use_window variant is not implemented (SURVEY 8f-4)")
+        # data.use_window is a re-layout DiffusionUNet.forward applies around the engine (the engine sees [P, 6 p^2, R, R])
         if getattr(config.data, "global_attn", False):
             raise NotImplementedError("global_attn (DiffusionUNet_Global) is out of scope")
         if float(getattr(config.model, "dropout", 0.0)) != 0.0:

@@ -123,9 +123,9 @@ class DiffusionUNet(nn.Module):
         self.use_window = config.data.use_window
         self.window_size = config.data.window_size
         self.use_wavelet_in_unet = config.data.wavelet_in_unet
-        if self.use_window:
-            raise NotImplementedError("the use_window UNet variant is not implemented "
-                                      "(unused by raindrop_wavelet.yml; SURVEY.md 8f-4)")
+        if self.use_window and self.use_wavelet_in_unet:
+            raise NotImplementedError("use_window together with wavelet_in_unet: the reference applies both re-layouts "
+                                      "in sequence (unet.py:347-350) and no channel count satisfies both; unused")
         if self.use_wavelet_in_unet:
             # models/unet.py:203-206 -- created first, as in the reference (module order = state-dict / RNG order)
             from .wavelet import WaveletTransform
@@ -226,7 +226,35 @@ class DiffusionUNet(nn.Module):
             self._engines[precision] = eng
         return eng
 
+    # ------------------------------------------------------------------------------------------ use_window
+    # data.use_window (models/unet.py:309-336,347-348,391-392): the 3-channel halves of the input are cut into p x p
+    # tiles of side R that become channels (tile-major space-to-depth), the network runs on [P, 6 p^2, R, R], and its
+    # [P, 3 p^2, R, R] output is pasted back to [P, 3, pR, pR]. Pure index re-layouts around the same engine.
+    @staticmethod
+    def to_win(x, p):
+        B, C, H, W = x.shape
+        return x.view(B, C, p, H // p, p, W // p).permute(0, 1, 2, 4, 3, 5).contiguous().view(B, -1, H // p, W // p)
+
+    @staticmethod
+    def win_back(x, p):
+        B, C, H, W = x.shape
+        return x.view(B, C // (p * p), p, p, H, W).permute(0, 1, 2, 4, 3, 5).contiguous().view(B, C // (p * p), H * p, W * p)
+
+    def convert_image_to_patches(self, x):
+        p = self.window_size
+        return torch.cat([self.to_win(x[:, :3], p), self.to_win(x[:, 3:], p)], dim=1)
+
+    def convert_patches_to_image(self, x):
+        return self.win_back(x, self.window_size)
+
     def forward(self, x, t):
+        if self.use_window:
+            # pixel-domain [P, 6, pR, pR] in, [P, 3, pR, pR] out (the reference asserts after the re-layout, :351)
+            assert x.shape[2] == x.shape[3] == self.resolution * self.window_size
+            xw = self.convert_image_to_patches(x)
+            if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+                return self.convert_patches_to_image(self._forward_autograd(xw, t))
+            return self.convert_patches_to_image(self.engine().forward(xw, t))
         # wavelet_in_unet: pixel-domain [P, 6, 4R, 4R] in, [P, 3, 4R, 4R] out (the reference asserts after its DWT, :351)
         side = self.resolution * (4 if self.use_wavelet_in_unet else 1)
         assert x.shape[2] == x.shape[3] == side
