@@ -52,5 +52,14 @@ done
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"dwt4x4|iwt4x4" \
     -c 60 --csv --log-file $O/${TAG}_dwt_dram.csv python tools/bench_dwt.py > $O/${TAG}_dwt_ncu.log 2>&1
 timeout 300 python tools/bench_dwt.py > $O/${TAG}_bench_dwt.txt 2>&1
+
+# 5. HFRM engine: per-kernel launch list of one call (B = 64, 256x256, bf16) + timing
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"hfrm_|gemm_tc" -c 700 --csv \
+    --log-file $O/${TAG}_hfrm_launches.csv python tools/bench_hfrm.py --precisions bf16 --iters 1 > $O/${TAG}_hfrm_ncu.log 2>&1
+python tools/hfrm_launch_summary.py $O/${TAG}_hfrm_launches.csv > $O/${TAG}_hfrm_launch_summary.txt 2>&1
+timeout 300 python tools/bench_hfrm.py > $O/${TAG}_bench_hfrm.txt 2>&1
+# 6. per-step GPU timeline of the sampler + single-image latency
+timeout 300 python tools/sampler_timeline.py 2>&1 | tail -6 > $O/${TAG}_sampler_timeline.txt
+timeout 300 python tools/latency_small.py > $O/${TAG}_latency_small.txt 2>&1
 du -sh $O
 ls -la $O | grep ${TAG}_ | head -40
