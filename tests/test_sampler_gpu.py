@@ -122,6 +122,39 @@ def _make_diffusion(tmp_path, precision, steps):
     return diffusion, DiffusiveRestoration(diffusion, args, cfg), cfg
 
 
+def test_restore_batch_with_hfrm_branch_vs_oracle_pipeline(tmp_path):
+    """The complete restore() computation (restoration.py:73-135) INCLUDING the HFRM branch, as bench.py now times it:
+    HFRM(cond) -> data_transform -> DWT -> x_other = bands [3:), 6 DDIM steps, x0_preds[-5], cat with the HFRM's high bands,
+    IWT, clamp -- against the same pipeline assembled from the oracles (hfrm_oracle + dwt_oracle + unet_oracle) on the CPU.
+    The HFRM parameters are randomised (default init leaves beta / gamma at zero = an identity network)."""
+    from oracle import dwt_oracle as DO
+    from oracle import hfrm_oracle as HO
+    diffusion, restorer, cfg = _make_diffusion(str(tmp_path), "fp32", 6)
+    hsd = {k: v * 0.5 for k, v in HO.fill_params(HO.default_shapes(), 17).items()}   # refinement of +-0.6 on a [0, 1] image
+    diffusion.generator.load_state_dict(hsd, strict=True)
+    gen = torch.Generator().manual_seed(21)
+    ximg = torch.rand(1, 6, 256, 256, generator=gen)
+    noise = torch.randn(1, 3, 64, 64, generator=gen)
+    res = restorer.restore_batch(ximg, r=16, noise=noise.to(DEV), want_variants=True)
+    out = res["output"].cpu()
+    # oracle pipeline
+    sd = O.init_state_dict(cfg, seed=61)
+    with torch.no_grad():
+        cond = ximg[:, :3].contiguous()
+        wd = HO.hfrm_forward(hsd, cond)
+        x_cond = torch.from_numpy(DO.dwt(cond.numpy(), flags=1))
+        wd_wav = torch.from_numpy(DO.dwt(wd.contiguous().numpy(), flags=1))
+        x_other = wd_wav[:, 3:].contiguous()
+        _, x0p = O.ddim_sample_overlapping(lambda a, tt: O.unet_forward(sd, cfg, a, tt), noise, x_cond, x_other,
+                                           O.sampling_seq(1000, 6), O.beta_schedule(cfg), [(0, 0)], 64)
+        ref = torch.from_numpy(DO.iwt(torch.cat([x0p[-5][:, :3], wd_wav[:, 3:]], 1).numpy(), flags=1))
+    d_wd = float((res["all_wdnet"].cpu() - wd).abs().max()) / float(wd.abs().max())
+    d_img = float((out - ref).abs().max())
+    print(f"restore_batch with HFRM: HFRM output max rel {d_wd:.2e}, final image max |d| {d_img:.2e}")
+    assert d_wd <= 5e-5
+    assert d_img < 1e-3
+
+
 def test_sandwich_full_fp32_vs_reference_golden(tmp_path):
     """Config #1 of BASELINE.json (1 image 256x256, 10 DDIM steps) against what the reference's own
     classes produced: same x0_preds[-5] element, final image |d| < 1e-3, PSNR within 0.01 dB."""

@@ -48,9 +48,15 @@ for skip in 8 40 100 160; do
     rm -f $O/${TAG}_full_$i.ncu-rep   # gpurun_out/ is capped at 64 MiB: only the extracted summaries travel back
 done
 
-# 4. DWT / IWT at B = 256 (3 x 403 MB rotating buffers): DRAM bytes per launch next to the algorithmic 402 653 184 B
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"dwt4x4|iwt4x4" \
-    -c 60 --csv --log-file $O/${TAG}_dwt_dram.csv python tools/bench_dwt.py > $O/${TAG}_dwt_ncu.log 2>&1
+# 4. DWT / IWT at B = 256 (3+ x 403 MB rotating buffers): DRAM bytes per launch next to the algorithmic 402 653 184 B.
+#    bench_dwt.py launches every kernel 45 times per shape, B = 64 first: skipping 50 launches of one kernel lands in B = 256
+: > $O/${TAG}_dwt_dram.csv
+for k in dwt4x4_direct iwt4x4_direct; do
+    timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:$k \
+        -s 50 -c 8 --csv --log-file $O/${TAG}_dwt_dram_$k.csv python tools/bench_dwt.py > $O/${TAG}_dwt_ncu.log 2>&1
+    grep -v "^==" $O/${TAG}_dwt_dram_$k.csv >> $O/${TAG}_dwt_dram.csv
+    rm -f $O/${TAG}_dwt_dram_$k.csv
+done
 timeout 300 python tools/bench_dwt.py > $O/${TAG}_bench_dwt.txt 2>&1
 
 # 5. HFRM engine: per-kernel launch list of one call (B = 64, 256x256, bf16) + timing
