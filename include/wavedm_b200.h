@@ -128,7 +128,9 @@ typedef struct wdm_unet wdm_unet_t;
 WDM_API int wdm_unet_param_count(const wdm_unet_config* cfg);
 /* i-th parameter tensor in canonical order: its state_dict name (NUL-terminated into name[0..cap)) and numel. */
 WDM_API int wdm_unet_param_info(const wdm_unet_config* cfg, int i, char* name, int cap, long long* numel);
+/* upper bound over the engine flags (WDM_PREC_FP32: includes the WDM_ENGINE_TC32 split weights); _flags: exact */
 WDM_API size_t wdm_unet_packed_bytes(const wdm_unet_config* cfg, int precision);
+WDM_API size_t wdm_unet_packed_bytes_flags(const wdm_unet_config* cfg, int precision, int flags);
 WDM_API int wdm_unet_create(const wdm_unet_config* cfg, int precision, int flags, const float* flat_params,
                             long long flat_numel, void* packed, size_t packed_bytes, void* stream,
                             wdm_unet_t** out);

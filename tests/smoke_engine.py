@@ -31,3 +31,18 @@ def run(dev) -> None:
     _, x0h = DdimSampler(eng).sample(x0, xc, xo, seq, betas, corners, 16)
     err = (x0h[-1].cpu() - x0p[-1]).abs().max().item()
     assert err < 1e-3 * x0p[-1].abs().max().item(), f"DDIM mismatch vs oracle: {err}"
+
+    # HFRM engine (restore()'s once-per-image refinement CNN) vs its oracle, and the batched PSNR statistics kernel
+    from oracle import hfrm_oracle as HO
+    from wavedm_b200 import metrics
+    from wavedm_b200.hfrm import HfrmEngine
+    hsd = {k: v * 0.5 for k, v in HO.fill_params(HO.default_shapes(), 3).items()}
+    xi = torch.rand(2, 3, 32, 48, generator=g)
+    href = HO.hfrm_forward(hsd, xi)
+    for prec, tol in (("fp32", 1e-5), ("bf16", 3e-2)):
+        y = HfrmEngine(hsd, dev, precision=prec).forward(xi.to(dev)).cpu()
+        rel = ((y - href).norm() / href.norm()).item()
+        assert rel < tol, f"HFRM {prec} mismatch vs oracle: rel {rel}"
+    ps = metrics.psnr_batch(xi.to(dev), href.to(dev))[0]
+    for b in range(2):
+        assert abs(ps[b] - float(metrics.torchPSNR(xi[b:b + 1], href[b:b + 1]))) < 1e-3, "PSNR kernel mismatch"

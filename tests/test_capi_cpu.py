@@ -70,7 +70,7 @@ def test_unet_config_validation_and_parameter_table_without_a_device():
     assert dict(tw)["conv_out.weight"] == 48 * 128 * 9
     cw.out_ch = 3   # wavelet_in_unet needs 48 output channels
     assert lib.wdm_unet_param_count(ctypes.byref(cw)) == _lib.WDM_ERR_BAD_ARG
-    cs.out_ch = 48  # and the plain mode at most 4
+    cs.out_ch = 65  # and the plain mode at most 64 (out_ch = 3 p^2 of data.use_window)
     assert lib.wdm_unet_param_count(ctypes.byref(cs)) == _lib.WDM_ERR_BAD_ARG
     # the fused restore() epilogue kernel validates shapes before touching the device
     buf = (ctypes.c_float * 64)()

@@ -86,6 +86,7 @@ def load() -> ctypes.CDLL:
         "wdm_unet_param_count": (c_int, [c_void_p]),
         "wdm_unet_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, c_void_p]),
         "wdm_unet_packed_bytes": (c_size_t, [c_void_p, c_int]),
+        "wdm_unet_packed_bytes_flags": (c_size_t, [c_void_p, c_int, c_int]),
         "wdm_unet_create": (c_int, [c_void_p, c_int, c_int, c_void_p, c_longlong, c_void_p, c_size_t, c_void_p,
                                     c_void_p]),
         "wdm_unet_destroy": (None, [c_void_p]),

@@ -1096,6 +1096,17 @@ extern "C" size_t wdm_unet_packed_bytes(const wdm_unet_config* cfg, int precisio
     return total;
 }
 
+extern "C" size_t wdm_unet_packed_bytes_flags(const wdm_unet_config* cfg, int precision, int flags) {
+    if (!cfg || (precision != WDM_PREC_FP32 && precision != WDM_PREC_BF16)) return 0;
+    wdm_unet net;
+    if (build_model(*cfg, &net.model) != WDM_OK) return 0;
+    net.dt = precision == WDM_PREC_FP32 ? DT_F32 : DT_BF16;
+    net.flags = flags;
+    size_t total = 0;
+    pack_model(&net, nullptr, 0, &total);
+    return total;
+}
+
 extern "C" int wdm_unet_create(const wdm_unet_config* cfg, int precision, int flags, const float* flat_params,
                                long long flat_numel, void* packed, size_t packed_bytes, void* stream,
                                wdm_unet_t** out) {

@@ -128,7 +128,7 @@ class UNetEngine:
         if extra:
             raise KeyError(f"unexpected keys in state_dict: {sorted(extra)[:5]} ...")
         flat = torch.cat(chunks)
-        nbytes = self.lib.wdm_unet_packed_bytes(ctypes.byref(self.cstruct), self.prec)
+        nbytes = self.lib.wdm_unet_packed_bytes_flags(ctypes.byref(self.cstruct), self.prec, flags)
         if nbytes == 0:
             raise _lib.WdmError(_lib.WDM_ERR_BAD_ARG, "wdm_unet_packed_bytes")
         self.packed = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
