@@ -42,10 +42,11 @@ def test_hfrm_fp32_and_bf16_vs_reference_golden():
     assert r16 <= 2e-2
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 16, 16), (3, 64, 96), (2, 256, 256)])
+@pytest.mark.parametrize("B,H,W", [(1, 16, 16), (3, 64, 96), (2, 256, 256), (1, 480, 720)])
 def test_hfrm_vs_oracle_shapes(B, H, W):
     """Seeded parameters / inputs at sizes the CPU oracle finishes in seconds: the smallest legal image (one pixel at the
-    deepest level), a ragged batch of non-square images, and the BASELINE 256 x 256 size."""
+    deepest level), a ragged batch of non-square images, the BASELINE 256 x 256 size, and the real RainDrop geometry
+    (480 x 720: 30 x 45 pixels at the deepest level, row counts that are no multiple of the 128-row tensor-core tile)."""
     from oracle import hfrm_oracle as HO
     sd = HO.fill_params(_shapes(ARCH), 71)
     x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(5))

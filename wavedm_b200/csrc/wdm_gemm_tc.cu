@@ -954,7 +954,10 @@ struct Cfg2 {
     static constexpr int kSmem = kStages * kStage + 1024 + kTail;
 };
 
-template <int BN, int MT = 1, int GRP = 2, bool PB = false>
+// HELP (with PB): the mbarrier.try_wait on the operand barriers (187 cycles even when the barrier is already complete, see
+// tools/mma_rate.cu) moves off the MMA-issuing thread: warp 11 of the leader CTA waits on full[] in order and publishes the
+// number of landed issue groups in shared memory (st.release); the issuer polls that word (ld.acquire, ~30 cycles).
+template <int BN, int MT = 1, int GRP = 2, bool PB = false, bool HELP = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB,
@@ -968,6 +971,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     uint64_t* tfull = bars + 2 * C::kStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint32_t* ready = tmem_slot + 1;  // HELP: issue groups whose operands have landed (leader CTA)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
@@ -992,6 +996,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             ptx::mbar_init(&tfull[s], 1);
             ptx::mbar_init(&tempty[s], 2 * kEpiThreads);  // the epilogue threads of both CTAs (only the leader's copy is used)
         }
+        *ready = 0;
         ptx::fence_mbar_init();
     }
     if (warp == kWarpAlloc) {
@@ -1104,7 +1109,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                         const uint32_t gq = tl * (uint32_t)((kblocks + 1) / 2) + (uint32_t)(kb >> 1);
                         pslot = gq % np;
                         sidx[0] = 2 * pslot, sidx[GRP - 1] = 2 * pslot + 1;
-                        ptx::mbar_wait(&full[pslot], (gq / np) & 1);
+                        if (HELP) {
+                            uint32_t spins = 0, seen;
+                            do {
+                                asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(ptx::smem_u32(ready)) : "memory");
+                                if (++spins > (1u << 28)) __trap();  // a broken protocol must not hang the GPU
+                            } while ((int32_t)(seen - gq) <= 0);
+                        } else {
+                            ptx::mbar_wait(&full[pslot], (gq / np) & 1);
+                        }
                     } else {
 #pragma unroll
                     for (int j = 0; j < GRP; ++j) {
@@ -1146,6 +1159,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     __syncwarp();
                     kb += nb;
                     it += nb;
+                }
+            }
+        }
+    } else if (HELP && PB && warp == 11) {
+        // ------------------------------------------------------------------ barrier helper (leader CTA only)
+        if (leader && lane == 0) {
+            constexpr uint32_t np = C::kStages / 2;
+            const uint32_t groups = (uint32_t)((kblocks + 1) / 2);
+            uint32_t gq = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += nclusters) {
+                for (uint32_t gi = 0; gi < groups; ++gi) {
+                    ptx::mbar_wait(&full[gq % np], (gq / np) & 1);
+                    ++gq;
+                    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(ptx::smem_u32(ready)), "r"(gq) : "memory");
                 }
             }
         }
@@ -1262,16 +1289,16 @@ int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& A
     return wdm_launch_status();
 }
 
-template <int BN, int MT = 1, int GRP = 2, bool PB = false>
+template <int BN, int MT = 1, int GRP = 2, bool PB = false, bool HELP = false>
 int launch_pair(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& A2, const CUtensorMap& B, const CUtensorMap& O,
                 const TcArgs& a, cudaStream_t s) {
     using C = Cfg2<BN, MT>;
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, MT, GRP, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, MT, GRP, PB, HELP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     const int tiles = ((a.m_tiles + 2 * MT - 1) / (2 * MT)) * a.n_tiles;
     const int pairs = num_sms_tc() / 2;
     const int grid = 2 * (tiles < pairs ? tiles : pairs);
-    e = wdm_launch_pdl(gemm_tc2_kernel<BN, MT, GRP, PB>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, A2, B, O, a);
+    e = wdm_launch_pdl(gemm_tc2_kernel<BN, MT, GRP, PB, HELP>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, A2, B, O, a);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
     return wdm_launch_status();
 }
@@ -1569,6 +1596,13 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
             const char* e = getenv("WDM_TC_PAIRBAR");
             return e ? atoi(e) : 1;  // measured: UNet call 5.15 -> 4.82 ms (the issuing thread was the bottleneck)
         }();
+        static const int helper = []() {
+            const char* e = getenv("WDM_TC_HELPER");
+            return e ? atoi(e) : 0;
+        }();
+        if (pairbar && helper)  // + the operand-barrier waits on a helper warp
+            return pair192 ? launch_pair<192, 1, 2, true, true>(A0, A1, A2, B, O, a, s)
+                           : launch_pair<256, 1, 2, true, true>(A0, A1, A2, B, O, a, s);
         if (pairbar)  // one full / empty barrier per two-k-block issue group
             return pair192 ? launch_pair<192, 1, 2, true>(A0, A1, A2, B, O, a, s) : launch_pair<256, 1, 2, true>(A0, A1, A2, B, O, a, s);
         return pair192 ? launch_pair<192>(A0, A1, A2, B, O, a, s) : launch_pair<256>(A0, A1, A2, B, O, a, s);

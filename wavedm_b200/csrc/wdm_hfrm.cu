@@ -982,53 +982,57 @@ __global__ void __launch_bounds__(256, 2) hfrm_dw_gate_kernel(const T* __restric
     const T* base = in + img * H * W * 2 * C;
     T* obase = out + img * H * W * C;
     const int r_last = ty0 + kDwTH < H ? ty0 + kDwTH : H;  // last input row needed (row H is the zero padding row)
-    // clamped offsets of x - 1, x, x + 1
-    long long xoff[3];
+    // 32-bit element offsets inside the image (the launcher checks H*W*2C < 2^31) and running row offsets: the address
+    // arithmetic of the six loads and the store is one add + one widening multiply-add each
+    int xoff[3], xoff2[3];
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
-        const int xx = x + dx - 1, xc = xx < 0 ? 0 : (xx >= W ? W - 1 : xx);
-        xoff[dx] = (long long)xc * 2 * C + c;
+        const int xx = x + dx - 1, xc = xx < 0 ? 0 : (xx >= W ? W - 1 : xx);  // clamped: out-of-image columns have zero weights
+        xoff[dx] = xc * 2 * C + c;
+        xoff2[dx] = xoff[dx] + C;
     }
-    // raw loads of input row r (clamped address; the mask is applied when the row is consumed): issued TWO rows ahead of
-    // their use so that 18 loads per thread are in flight -- the kernel is DRAM-latency bound otherwise
-    auto fetch = [&](int r, float (&v)[3][4]) {
-        if (r > r_last) return;
-        const int rc = r < 0 ? 0 : (r >= H ? H - 1 : r);
-        const T* row = base + (long long)rc * W * 2 * C;
+    const int rowpitch = W * 2 * C, opitch = W * C;
+    int roff = (ty0 - 1) * rowpitch;       // offset of the next row to fetch
+    int rf = ty0 - 1;                      // ... and its index
+    int ooff = (ty0 - 1) * opitch + x * C + c;  // offset of output row (r - 1) for the step of input row r = ty0
+    // raw loads of the next input row, issued TWO rows ahead of their use so that 18 loads per thread are in flight; rows
+    // outside the image are not loaded at all (their step skips the accumulation; r is uniform over the CTA)
+    auto fetch = [&](float (&v)[3][4]) {
+        if (rf >= 0 && rf < H && rf <= r_last) {
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            load2(row + xoff[dx], v[dx][0], v[dx][1]);
-            load2(row + xoff[dx] + C, v[dx][2], v[dx][3]);
+            for (int dx = 0; dx < 3; ++dx) {
+                load2(base + (roff + xoff[dx]), v[dx][0], v[dx][1]);
+                load2(base + (roff + xoff2[dx]), v[dx][2], v[dx][3]);
+            }
         }
+        ++rf, roff += rowpitch;
     };
     auto step = [&](int r, float (&v)[3][4], auto ph) {
         constexpr int PH = decltype(ph)::value;
         if (r > r_last) return;
-        // rows above / below the image contribute nothing (r is uniform over the CTA: no divergence); out-of-image COLUMNS
-        // read the clamped pixel against weights that were zeroed once, above
         if (r >= 0 && r < H) dw_accumulate<PH>(acc, v, w);
         // output row r - 1 has now seen its three input rows
         constexpr int DONE = (PH + 2) % 3;
-        const int ro = r - 1;
-        if (ro >= ty0 && active) {
+        if (r - 1 >= ty0 && active) {
             const float g0 = acc[DONE][0] * acc[DONE][2], g1 = acc[DONE][1] * acc[DONE][3];
-            store2(obase + ((long long)ro * W + x) * C + c, g0, g1);
+            store2(obase + ooff, g0, g1);
             sum0 += g0, sum1 += g1;
         }
+        if (r >= ty0) ooff += opitch;
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[DONE][e] = b4[e];
     };
     // input rows ty0 - 1 .. r_last; the phase of a row is (row - (ty0 - 1)) mod 3 = the register buffer it was fetched into
     float va[3][4], vb[3][4], vc[3][4];
-    fetch(ty0 - 1, va);
-    fetch(ty0, vb);
+    fetch(va);
+    fetch(vb);
     for (int i = 0; i < kDwTH + 2; i += 3) {
         const int r = ty0 - 1 + i;
-        fetch(r + 2, vc);
+        fetch(vc);
         step(r, va, std::integral_constant<int, 0>());
-        fetch(r + 3, va);
+        fetch(va);
         step(r + 1, vb, std::integral_constant<int, 1>());
-        fetch(r + 4, vb);
+        fetch(vb);
         step(r + 2, vc, std::integral_constant<int, 2>());
     }
     red[tid * 2] = sum0, red[tid * 2 + 1] = sum1;
@@ -1555,6 +1559,10 @@ int hfrm_forward_t(wdm_hfrm* net, HArena& ar, const float* x, int B, int H, int 
         }
         if (st != WDM_OK) return;
         const int tiles_x = wdm_cdiv(w, dw_tile_w(C)), tiles = tiles_x * wdm_cdiv(h, kDwTH);
+        if ((long long)h * w * 2 * C >= (1LL << 31)) {  // the depthwise kernel indexes one image with 32-bit offsets
+            st = WDM_ERR_BAD_SHAPE;
+            return;
+        }
         hfrm_dw_gate_kernel<T><<<dim3(tiles, B, C > kDwCS ? C / kDwCS : 1), 256, 0, s>>>(t1, b.dw_w, b.dw_b, t2, partial, C, h, w, tiles_x);
         st = wdm_launch_status();
         if (st != WDM_OK) return;
