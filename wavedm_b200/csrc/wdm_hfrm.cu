@@ -941,11 +941,15 @@ __device__ __forceinline__ void dw_accumulate(float (&acc)[3][4], const float (&
         }
 }
 
-template <typename T>
+// CT > 0: the channel count as a compile-time constant (C = 32 / 64, the full / half resolution levels that carry 75 % of
+// this kernel's time): neighbour-pixel and partner-half offsets become immediates of the load instructions -- the generic
+// form spent two thirds of its issue slots on address arithmetic.
+template <typename T, int CT>
 __global__ void __launch_bounds__(256, 2) hfrm_dw_gate_kernel(const T* __restrict__ in, const float* __restrict__ w9 /*[9][2C]*/,
                                                           const float* __restrict__ bias /*[2C]*/, T* __restrict__ out,
-                                                          float* __restrict__ partial /*[B][tiles][C]*/, int C, int H, int W,
+                                                          float* __restrict__ partial /*[B][tiles][C]*/, int C_rt, int H, int W,
                                                           int tiles_x) {
+    const int C = CT ? CT : C_rt;
     __shared__ float red[256 * 2];
     const int CS = C < kDwCS ? C : kDwCS, c0 = blockIdx.z * CS, PP = CS >> 1, TW = 256 / PP;
     const int tid = threadIdx.x, cp = tid % PP, xl = tid / PP;
@@ -982,30 +986,21 @@ __global__ void __launch_bounds__(256, 2) hfrm_dw_gate_kernel(const T* __restric
     const T* base = in + img * H * W * 2 * C;
     T* obase = out + img * H * W * C;
     const int r_last = ty0 + kDwTH < H ? ty0 + kDwTH : H;  // last input row needed (row H is the zero padding row)
-    // 32-bit element offsets inside the image (the launcher checks H*W*2C < 2^31) and running row offsets: the address
-    // arithmetic of the six loads and the store is one add + one widening multiply-add each
-    int xoff[3], xoff2[3];
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-        const int xx = x + dx - 1, xc = xx < 0 ? 0 : (xx >= W ? W - 1 : xx);  // clamped: out-of-image columns have zero weights
-        xoff[dx] = xc * 2 * C + c;
-        xoff2[dx] = xoff[dx] + C;
-    }
+    // one running pointer to (row, x) of this thread's channel pair; the neighbours x - 1 / x + 1 and the partner half sit at
+    // fixed element offsets from it (-2C, +2C, +C). Out-of-image columns are predicated off (their weights are zero and the
+    // registers keep a finite earlier value); rows outside the image are not loaded at all (r is uniform over the CTA)
+    const bool vx0 = active && x >= 1, vx1 = active, vx2 = active && x + 1 < W;
     const int rowpitch = W * 2 * C, opitch = W * C;
-    int roff = (ty0 - 1) * rowpitch;       // offset of the next row to fetch
-    int rf = ty0 - 1;                      // ... and its index
+    const T* rp = base + ((long long)(ty0 - 1) * rowpitch + (long long)(active ? x : 0) * 2 * C + c);  // may point before row 0: not
+    int rf = ty0 - 1;                                                                                // dereferenced then
     int ooff = (ty0 - 1) * opitch + x * C + c;  // offset of output row (r - 1) for the step of input row r = ty0
-    // raw loads of the next input row, issued TWO rows ahead of their use so that 18 loads per thread are in flight; rows
-    // outside the image are not loaded at all (their step skips the accumulation; r is uniform over the CTA)
     auto fetch = [&](float (&v)[3][4]) {
         if (rf >= 0 && rf < H && rf <= r_last) {
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                load2(base + (roff + xoff[dx]), v[dx][0], v[dx][1]);
-                load2(base + (roff + xoff2[dx]), v[dx][2], v[dx][3]);
-            }
+            if (vx0) load2(rp - 2 * C, v[0][0], v[0][1]), load2(rp - C, v[0][2], v[0][3]);
+            if (vx1) load2(rp, v[1][0], v[1][1]), load2(rp + C, v[1][2], v[1][3]);
+            if (vx2) load2(rp + 2 * C, v[2][0], v[2][1]), load2(rp + 3 * C, v[2][2], v[2][3]);
         }
-        ++rf, roff += rowpitch;
+        ++rf, rp += rowpitch;
     };
     auto step = [&](int r, float (&v)[3][4], auto ph) {
         constexpr int PH = decltype(ph)::value;
@@ -1023,7 +1018,7 @@ __global__ void __launch_bounds__(256, 2) hfrm_dw_gate_kernel(const T* __restric
         for (int e = 0; e < 4; ++e) acc[DONE][e] = b4[e];
     };
     // input rows ty0 - 1 .. r_last; the phase of a row is (row - (ty0 - 1)) mod 3 = the register buffer it was fetched into
-    float va[3][4], vb[3][4], vc[3][4];
+    float va[3][4] = {}, vb[3][4] = {}, vc[3][4] = {};
     fetch(va);
     fetch(vb);
     for (int i = 0; i < kDwTH + 2; i += 3) {
@@ -1035,6 +1030,122 @@ __global__ void __launch_bounds__(256, 2) hfrm_dw_gate_kernel(const T* __restric
         fetch(vb);
         step(r + 2, vc, std::integral_constant<int, 2>());
     }
+    red[tid * 2] = sum0, red[tid * 2 + 1] = sum1;
+    __syncthreads();
+    for (int ch = tid; ch < CS; ch += 256) {
+        float sacc = 0.f;
+        for (int q = 0; q < TW; ++q) sacc += red[(q * PP + (ch >> 1)) * 2 + (ch & 1)];  // fixed order: deterministic
+        partial[(img * gridDim.x + blockIdx.x) * C + c0 + ch] = sacc;
+    }
+}
+
+// The same computation with the input staged through shared memory: the register-streaming kernel above keeps only
+// ~12 KiB of unique DRAM bytes in flight per SM (16 warps x 3 rows x 2 pixels) and runs at 1.3 TB/s whatever its instruction
+// count. Here all 256 threads cp.async whole bands of kDwRB rows x (TW + 2) pixels x 2 x CS channels into a 4-deep ring
+// (three bands = ~40 KiB per CTA in flight), zero-filling everything outside the image (so the compute needs no masks), and
+// the column threads read their 3 x 2 values per row from the ring.
+constexpr int kDwRB = 4, kDwNB = 4;
+template <typename T>
+__host__ __device__ constexpr int dw_px_stride(int CS) {  // bytes per staged pixel; C = 32: +64 so that the two pixels of a warp
+    return 2 * CS * (int)sizeof(T) + ((2 * CS * (int)sizeof(T)) % 256 == 0 ? 0 : 64);  // hit different banks
+}
+template <typename T>
+__host__ __device__ constexpr int dw_band_bytes(int CS) { return kDwRB * (256 / (CS / 2) + 2) * dw_px_stride<T>(CS); }
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) hfrm_dw_gate_smem_kernel(const T* __restrict__ in, const float* __restrict__ w9,
+                                                               const float* __restrict__ bias, T* __restrict__ out,
+                                                               float* __restrict__ partial, int C, int H, int W, int tiles_x) {
+    extern __shared__ __align__(128) unsigned char dsm_raw[];
+    __shared__ float red[256 * 2];
+    const int CS = C < kDwCS ? C : kDwCS, c0 = blockIdx.z * CS, PP = CS >> 1, TW = 256 / PP;
+    const int PS = dw_px_stride<T>(CS), band_bytes = kDwRB * (TW + 2) * PS;
+    const int tid = threadIdx.x, cp = tid % PP, xl = tid / PP;
+    const int c = c0 + 2 * cp;
+    const long long img = blockIdx.y;
+    const int ty0 = (blockIdx.x / tiles_x) * kDwTH, tx0 = (blockIdx.x % tiles_x) * TW, x = tx0 + xl;
+    const bool active = x < W;
+    float w[9][4], b4[4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const float2 a = *reinterpret_cast<const float2*>(w9 + t * 2 * C + c), d = *reinterpret_cast<const float2*>(w9 + t * 2 * C + C + c);
+        w[t][0] = a.x, w[t][1] = a.y, w[t][2] = d.x, w[t][3] = d.y;
+    }
+    b4[0] = bias[c], b4[1] = bias[c + 1], b4[2] = bias[C + c], b4[3] = bias[C + c + 1];
+    float acc[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][e] = b4[e];
+    float sum0 = 0.f, sum1 = 0.f;
+    const T* base = in + img * H * W * 2 * C;
+    T* obase = out + img * H * W * C;
+    const int r_last = ty0 + kDwTH < H ? ty0 + kDwTH : H;
+    constexpr int EPV = 16 / (int)sizeof(T);          // elements per 16-byte vector
+    const int vph = CS / EPV;                         // vectors per half of a pixel
+    const int vpb = kDwRB * (TW + 2) * 2 * vph;       // vectors per band
+    const int nbands = (kDwTH + 2 + kDwRB - 1) / kDwRB;
+    auto issue = [&](int b) {
+        if (b < nbands) {
+            unsigned char* dst = dsm_raw + (b % kDwNB) * band_bytes;
+            for (int v = tid; v < vpb; v += 256) {
+                const int q = v % vph, hh = (v / vph) & 1, pp = (v / (2 * vph)) % (TW + 2), rr = v / (2 * vph * (TW + 2));
+                const int r = ty0 - 1 + b * kDwRB + rr, xx = tx0 - 1 + pp;
+                const bool ok = r >= 0 && r < H && xx >= 0 && xx < W;
+                const T* src = base + ((long long)(ok ? r : 0) * W + (ok ? xx : 0)) * 2 * C + hh * C + c0 + q * EPV;
+                cp_async16(dst + (rr * (TW + 2) + pp) * PS + (hh * CS + q * EPV) * (int)sizeof(T), src, ok);
+            }
+        }
+        cp_async_commit();
+    };
+    int ooff = (ty0 - 1) * (W * C) + x * C + c;
+    auto row = [&](const unsigned char* band, int rr, int r, auto ph) {
+        constexpr int PH = decltype(ph)::value;
+        if (r > r_last) return;
+        float v[3][4];
+        const unsigned char* p0 = band + (rr * (TW + 2) + xl) * PS + 2 * cp * (int)sizeof(T);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            load2(reinterpret_cast<const T*>(p0 + dx * PS), v[dx][0], v[dx][1]);
+            load2(reinterpret_cast<const T*>(p0 + dx * PS) + CS, v[dx][2], v[dx][3]);
+        }
+        dw_accumulate<PH>(acc, v, w);  // rows / columns outside the image were zero-filled by the loader
+        constexpr int DONE = (PH + 2) % 3;
+        if (r - 1 >= ty0 && active) {
+            const float g0 = acc[DONE][0] * acc[DONE][2], g1 = acc[DONE][1] * acc[DONE][3];
+            store2(obase + ooff, g0, g1);
+            sum0 += g0, sum1 += g1;
+        }
+        if (r >= ty0) ooff += W * C;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[DONE][e] = b4[e];
+    };
+    for (int b = 0; b < kDwNB - 1; ++b) issue(b);
+    // three bands (12 rows) per pass: the accumulator phase of a row, (row index) mod 3, is then a compile-time constant
+    for (int b0 = 0; b0 < nbands; b0 += 3) {
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) {
+            const int b = b0 + bb;
+            cp_async_wait<kDwNB - 2>();
+            __syncthreads();          // band b has landed for every thread; band b - 1 is free again
+            issue(b + kDwNB - 1);
+            if (b < nbands) {
+                const unsigned char* band = dsm_raw + (b % kDwNB) * band_bytes;
+                const int r = ty0 - 1 + b * kDwRB;
+                if (bb == 0) {
+                    row(band, 0, r, std::integral_constant<int, 0>()), row(band, 1, r + 1, std::integral_constant<int, 1>());
+                    row(band, 2, r + 2, std::integral_constant<int, 2>()), row(band, 3, r + 3, std::integral_constant<int, 0>());
+                } else if (bb == 1) {
+                    row(band, 0, r, std::integral_constant<int, 1>()), row(band, 1, r + 1, std::integral_constant<int, 2>());
+                    row(band, 2, r + 2, std::integral_constant<int, 0>()), row(band, 3, r + 3, std::integral_constant<int, 1>());
+                } else {
+                    row(band, 0, r, std::integral_constant<int, 2>()), row(band, 1, r + 1, std::integral_constant<int, 0>());
+                    row(band, 2, r + 2, std::integral_constant<int, 1>()), row(band, 3, r + 3, std::integral_constant<int, 2>());
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
     red[tid * 2] = sum0, red[tid * 2 + 1] = sum1;
     __syncthreads();
     for (int ch = tid; ch < CS; ch += 256) {
@@ -1563,7 +1674,29 @@ int hfrm_forward_t(wdm_hfrm* net, HArena& ar, const float* x, int B, int H, int 
             st = WDM_ERR_BAD_SHAPE;
             return;
         }
-        hfrm_dw_gate_kernel<T><<<dim3(tiles, B, C > kDwCS ? C / kDwCS : 1), 256, 0, s>>>(t1, b.dw_w, b.dw_b, t2, partial, C, h, w, tiles_x);
+        const dim3 dgrid(tiles, B, C > kDwCS ? C / kDwCS : 1);
+        static const int dw_smem = []() {
+            const char* e = getenv("WDM_HFRM_DW_SMEM");
+            return e ? atoi(e) : 1;
+        }();
+        if (dw_smem) {
+            const int ring = kDwNB * dw_band_bytes<T>(C < kDwCS ? C : kDwCS);
+            static bool attr = false;
+            if (!attr) {
+                cudaError_t e = cudaFuncSetAttribute(hfrm_dw_gate_smem_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+                if (e != cudaSuccess) {
+                    st = wdm_cuda_error((int)e);
+                    return;
+                }
+                attr = true;
+            }
+            hfrm_dw_gate_smem_kernel<T><<<dgrid, 256, ring, s>>>(t1, b.dw_w, b.dw_b, t2, partial, C, h, w, tiles_x);
+        } else if (C == 32)
+            hfrm_dw_gate_kernel<T, 32><<<dgrid, 256, 0, s>>>(t1, b.dw_w, b.dw_b, t2, partial, C, h, w, tiles_x);
+        else if (C == 64)
+            hfrm_dw_gate_kernel<T, 64><<<dgrid, 256, 0, s>>>(t1, b.dw_w, b.dw_b, t2, partial, C, h, w, tiles_x);
+        else
+            hfrm_dw_gate_kernel<T, 0><<<dgrid, 256, 0, s>>>(t1, b.dw_w, b.dw_b, t2, partial, C, h, w, tiles_x);
         st = wdm_launch_status();
         if (st != WDM_OK) return;
         hfrm_chan_kernel<<<dim3(B, wdm_cdiv(C, 64)), 256, (C + 256) * sizeof(float), s>>>(partial, tiles, C, 1.0f / (float)(h * w),
