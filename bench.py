@@ -399,13 +399,20 @@ def gpu_eager_baseline(dev, batch, ddim_sample_steps=3):
 
 def dram_traffic_per_launch():
     """roofline.traffic: dram__bytes_read + write per contraction launch from the committed ncu capture of ONE UNet call,
-    valid only for the library build it was taken on (the capture records the sha256 of libwavedm_b200.so)."""
+    valid only for the build it was taken on. Builds are identified by the hash of the library SOURCES (`_lib.source_id()`:
+    nvcc output is not byte-reproducible, so a rebuilt .so of the same sources has another file hash); captures of older
+    rounds that only recorded the .so hash match on that."""
     import hashlib
+    from wavedm_b200 import _lib
     try:
         with open(os.path.join(REPO, "wavedm_b200", "libwavedm_b200.so"), "rb") as f:
             sha = hashlib.sha256(f.read()).hexdigest()[:16]
     except Exception:
         sha = None
+    try:
+        src = _lib.source_id()
+    except Exception:
+        src = None
     best = None
     pdir = os.path.join(REPO, "profiles")
     for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
@@ -416,13 +423,15 @@ def dram_traffic_per_launch():
             except Exception:
                 continue
             d["file"] = "profiles/" + name
-            if d.get("lib_sha16") == sha:
-                return d["traffic_bytes_per_launch"], {"file": d["file"], "lib_sha16": sha, "same_build": True}
+            if (src and d.get("src_sha16") == src) or (sha and d.get("lib_sha16") == sha):
+                return d["traffic_bytes_per_launch"], {"file": d["file"], "src_sha16": d.get("src_sha16"),
+                                                       "lib_sha16": d.get("lib_sha16"), "same_build": True}
             best = d
     if best is not None:
-        return None, {"file": best["file"], "lib_sha16": best.get("lib_sha16"), "same_build": False,
-                      "stale_value": best.get("traffic_bytes_per_launch"), "this_lib_sha16": sha}
-    return None, {"this_lib_sha16": sha}
+        return None, {"file": best["file"], "src_sha16": best.get("src_sha16"), "lib_sha16": best.get("lib_sha16"),
+                      "same_build": False, "stale_value": best.get("traffic_bytes_per_launch"), "this_src_sha16": src,
+                      "this_lib_sha16": sha}
+    return None, {"this_src_sha16": src, "this_lib_sha16": sha}
 
 
 def dwt_roofline(dev, peak):

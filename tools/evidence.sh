@@ -8,6 +8,7 @@ TAG=${1:-r02}
 O=gpurun_out
 mkdir -p $O
 sha256sum wavedm_b200/libwavedm_b200.so | cut -c1-16 > $O/${TAG}_lib_sha16.txt
+python -c "from wavedm_b200 import _lib; print(_lib.source_id())" > $O/${TAG}_src_sha16.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > $O/${TAG}_smi.txt 2>&1
 
 # 1. launch list + DRAM bytes of one UNet call
@@ -30,6 +31,7 @@ import json, sys
 try:
     d = json.load(open(sys.argv[1]))
     d["lib_sha16"] = open(sys.argv[2]).read().strip()
+    d["src_sha16"] = open(sys.argv[2].replace("_lib_sha16", "_src_sha16")).read().strip()
     json.dump(d, open(sys.argv[1], "w"), indent=1)
 except Exception as e:
     print("traffic json:", e)

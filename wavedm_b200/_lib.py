@@ -60,6 +60,21 @@ def declared_symbols() -> List[str]:
     return re.findall(r"WDM_API\s+[\w\s\*]+?\b(wdm_\w+)\s*\(", src)
 
 
+def source_id() -> str:
+    """sha256[:16] over the CUDA / C sources the library is built from (csrc/*.cu, *.cuh, *.h and the C ABI header), in
+    name order. The build id measurement files are keyed on: nvcc output is not byte-reproducible, the sources are."""
+    import hashlib
+    h = hashlib.sha256()
+    src = os.path.join(_HERE, "csrc")
+    files = sorted(f for f in os.listdir(src) if f.endswith((".cu", ".cuh", ".h")))
+    for f in files:
+        with open(os.path.join(src, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    with open(HEADER_PATH, "rb") as fh:
+        h.update(b"wavedm_b200.h\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
 def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
