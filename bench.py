@@ -301,6 +301,14 @@ def parity_block(dev, precisions=("fp32", "fp32_ffma", "bf16"), batch=16, slots=
         r = restorer.restore_batch(xd, r=GRID_R, noise=noise.to(dev), x_other=x_other)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        # the same call again, timed on the device: throughput of this precision mode at the parity batch (HFRM bypassed)
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        nd = noise.to(dev)
+        e0.record()
+        restorer.restore_batch(xd, r=GRID_R, noise=nd, x_other=x_other)
+        e1.record()
+        torch.cuda.synchronize()
+        ips = batch / (e0.elapsed_time(e1) / 1e3)
         lat = r["latent"].cpu()[list(slots)]
         out = r["output"].cpu()[list(slots)]
         dps = [abs(float(torchPSNR(x[s_:s_ + 1, 3:], out[i:i + 1])) - float(g["psnr"][i])) for i, s_ in enumerate(slots)]
@@ -314,7 +322,7 @@ def parity_block(dev, precisions=("fp32", "fp32_ffma", "bf16"), batch=16, slots=
                      "image_max_abs_unsaturated_px": float((out - out_ref).abs()[unsat].max()) if unsat.any() else 0.0,
                      "unsaturated_px_frac": float(unsat.float().mean()),
                      "psnr_abs_diff_db": max(dps), "psnr_ref_db": [float(v) for v in g["psnr"]],
-                     "tc_launches": tc_n, "simt_launches": simt_n, "seconds": dt}
+                     "tc_launches": tc_n, "simt_launches": simt_n, "seconds": dt, "images_per_s": ips}
         res[prec]["pass"] = bool(res[prec]["image_max_abs"] < 1e-3 and res[prec]["psnr_abs_diff_db"] < 0.01)
         del restorer
         torch.cuda.empty_cache()
