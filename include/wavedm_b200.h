@@ -211,6 +211,12 @@ WDM_API int wdm_hfrm_forward(wdm_hfrm_t* net, const float* x, int B, int H, int 
 WDM_API int wdm_gather_patches(const float* src0, int C0, const float* src1, int C1, const float* src2, int C2, int B,
                                int h, int w, const int* patches, int P, int R, int Cpad, void* out, int out_dtype,
                                void* stream);
+/* In-place refresh of one source inside a tensor wdm_gather_patches produced: out[p, y, x, c_off + c] = src[img_p, c, ..]
+ * for c < C, all other channels kept. Between DDIM steps only x_t changes (models/ddm_wavelet.py:470-478 re-crops and
+ * re-concatenates x_cond / x_other every step although they are loop invariants): the sampler gathers once and then
+ * rewrites the C = 3 channels of x_t at c_off = channels(x_cond). */
+WDM_API int wdm_gather_patches_update(const float* src, int C, int c_off, int B, int h, int w, const int* patches, int P,
+                                      int R, int Cpad, void* out, int out_dtype, void* stream);
 /* wavelet_in_unet mode: crop + DWT + concat + NHWC in one kernel. src0 / src1: fp32 NCHW [B, 3, H, W] pixel-domain images
  * (already data_transform'ed), patches: (image, hi, wi) in PIXELS, patch side 4R; out: [P, R, R, Cpad], channel
  * s*48 + 3k + colour (models/unet.py:338-344 all_wavlet_dec on the crops of models/ddm_wavelet.py:467-478). */

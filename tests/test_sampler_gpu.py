@@ -372,3 +372,32 @@ def test_gather_patches_vs_torch(dtype, chans):
         got = out[q].float().cpu()
         assert torch.equal(got[..., :ctot], ref.to(td).float())
         assert not got[..., ctot:].any()
+
+
+@pytest.mark.parametrize("dtype", [0, 1])
+def test_gather_patches_update_rewrites_one_source_only(dtype):
+    """wdm_gather_patches_update == re-gathering with the new x_t: the sampler's per-step refresh (x_cond / x_other are loop
+    invariants of models/ddm_wavelet.py:467-478) is bit-identical to the whole gather, every other channel untouched."""
+    from wavedm_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(14)
+    B, h, w, R, Cpad = 2, 40, 56, 16, 128 if dtype else 96
+    chans = (48, 3, 45)
+    srcs = [torch.randn(B, c, h, w, generator=g).to(DEV) for c in chans]
+    xt_new = torch.randn(B, 3, h, w, generator=g).to(DEV)
+    pats = torch.tensor([[0, 0, 0], [1, 24, 40], [0, 7, 13], [1, 16, 3], [0, 24, 40]], dtype=torch.int32).to(DEV)
+    td = torch.bfloat16 if dtype else torch.float32
+    st = torch.cuda.current_stream().cuda_stream
+
+    def full(x_t):
+        out = torch.full((len(pats), R, R, Cpad), 5.0, dtype=td, device=DEV)
+        _lib.check(lib.wdm_gather_patches(srcs[0].data_ptr(), 48, x_t.data_ptr(), 3, srcs[2].data_ptr(), 45, B, h, w,
+                                          pats.data_ptr(), len(pats), R, Cpad, out.data_ptr(), dtype, st), "gather")
+        return out
+    out = full(srcs[1])
+    _lib.check(lib.wdm_gather_patches_update(xt_new.data_ptr(), 3, 48, B, h, w, pats.data_ptr(), len(pats), R, Cpad,
+                                             out.data_ptr(), dtype, st), "update")
+    assert torch.equal(out, full(xt_new))
+    # arguments that do not fit the tensor are refused
+    assert lib.wdm_gather_patches_update(xt_new.data_ptr(), 3, Cpad - 2, B, h, w, pats.data_ptr(), len(pats), R, Cpad,
+                                         out.data_ptr(), dtype, st) != 0

@@ -121,6 +121,8 @@ def load() -> ctypes.CDLL:
         "wdm_hfrm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
         "wdm_gather_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                        c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+        "wdm_gather_patches_update": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                              c_void_p, c_int, c_void_p]),
         "wdm_gather_patches_dwt": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                            c_void_p, c_int, c_void_p]),
         "wdm_iwt4x4_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -580,6 +580,23 @@ __global__ void __launch_bounds__(256) gather_patches_kernel(const GatherParams 
     }
 }
 
+// Refresh of ONE source's channels inside an already gathered tensor: out[p, y, x, c_off + c] = src[img_p, c, hi_p+y, wi_p+x],
+// every other channel untouched. The sampler's conditioning sources (x_cond, x_other: 93 of the 96 channels) do not
+// change between DDIM steps, only x_t (3 channels) does: steps 2..S move 6 B per pixel instead of re-gathering 256 B.
+template <typename TO>
+__global__ void __launch_bounds__(256) gather_update_kernel(const float* __restrict__ src, int C, int c_off, int h, int w,
+                                                            const int* __restrict__ patches, int R, int Cpad,
+                                                            TO* __restrict__ out) {
+    const int pi = blockIdx.y;
+    const int img = patches[pi * 3], hi = patches[pi * 3 + 1], wi = patches[pi * 3 + 2];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // pixel of the patch, x fastest
+    if (i >= R * R) return;
+    const int y = i / R, x = i - y * R;
+    TO* o = out + ((long long)pi * R * R + i) * Cpad + c_off;
+    const float* s = src + ((long long)img * C * h + (hi + y)) * w + (wi + x);
+    for (int c = 0; c < C; ++c) o[c] = TO(__ldg(s + (long long)c * h * w));
+}
+
 // ---------------------------------------------------------------------------------------------- DDIM step
 // One thread per image element. Every arithmetic step is an explicitly rounded fp32 op in the order torch
 // eager evaluates models/ddm_wavelet.py:496-502 (no FMA contraction) so the update is bit-identical to
@@ -869,6 +886,18 @@ int launch_gather_patches(const GatherParams& p, cudaStream_t s) {
                              96 * 1024);
         gather_patches_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>(p);
     }
+    return wdm_launch_status();
+}
+
+int launch_gather_update(const float* src, int C, int c_off, int h, int w, const int* patches, int P, int R, int Cpad,
+                         void* out, int out_dtype, cudaStream_t s) {
+    if (P <= 0 || C <= 0) return WDM_OK;
+    dim3 grid((R * R + 255) / 256, P);
+    if (out_dtype == DT_F32)
+        gather_update_kernel<float><<<grid, 256, 0, s>>>(src, C, c_off, h, w, patches, R, Cpad, reinterpret_cast<float*>(out));
+    else
+        gather_update_kernel<__nv_bfloat16>
+            <<<grid, 256, 0, s>>>(src, C, c_off, h, w, patches, R, Cpad, reinterpret_cast<__nv_bfloat16*>(out));
     return wdm_launch_status();
 }
 

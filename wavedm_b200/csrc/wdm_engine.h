@@ -83,6 +83,9 @@ struct GatherParams {
     int out_dtype;
 };
 int launch_gather_patches(const GatherParams& p, cudaStream_t stream);
+// one source's channels rewritten in place at channel offset c_off (x_t between DDIM steps)
+int launch_gather_update(const float* src, int C, int c_off, int h, int w, const int* patches, int P, int R, int Cpad,
+                         void* out, int out_dtype, cudaStream_t stream);
 // wavelet_in_unet (wdm_dwt.cu): fused crop + DWT + concat + NHWC gather, and the IWT of the NHWC conv_out result
 int launch_dwt_gather(const float* src0, const float* src1, int nsrc, int B, int H, int W, const int* patches, int P, int R,
                       int Cpad, void* out, int out_dtype, cudaStream_t stream);

@@ -77,6 +77,7 @@ struct TcArgs {
     int Wsrc;                  // subpix: source-grid width (epi_tma store box geometry)
     int split_cpp;             // tc32: 64-channel chunks per bf16 piece of segment 0 (0 = plain operands), see a_chunk()
     uint32_t split_tab;        // tc32: A piece of product pr in nibble pr
+    int pdl_late;              // the dependency wait moves into the roles (see the kernels)
 };
 
 // tc32 (fp32 emulated by a 3-way bf16 split, GemmParams::a_split3): the K loop of a tap walks SIX products
@@ -633,7 +634,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) tc_trace(a, 1);
-    wdm_grid_dependency_wait();  // PDL: everything above overlapped the previous kernel's tail
+    // PDL: everything above overlapped the previous kernel's tail. The dependency wait itself is per role (WDM_PDL_LATE):
+    // the producer first decodes its tile, takes the empty stage, posts the byte count and issues the WEIGHT tile (not written
+    // by the predecessor) and only then waits, right before its first activation load; the MMA issuer touches no global
+    // memory and does not wait at all; the epilogue warps wait at role entry (bias / timestep rows / residual / stores).
+    // Traced before: ~1 800 cycles between the wait and the first activation load of every launch.
+    if (!a.pdl_late) wdm_grid_dependency_wait();  // the per-role waits below then return at once
     if (threadIdx.x == 0) tc_trace(a, 2);
 
     const int num_tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;  // super-tiles of MT m-tiles
@@ -664,14 +670,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     if (lane == 0) {
                         uint8_t* sa = smem + s * C::kStage;
                         if (a.dbg == 1 || a.dbg == 9) {
+                            if (it == 0) wdm_grid_dependency_wait();
                             ptx::mbar_arrive(&full[s]);
                         } else {
                             ptx::mbar_arrive_expect_tx(&full[s], halo_bytes + 3 * C::kBBytes);
-                            ptx::tma_load_4d(sa, &tmA0, &full[s], a_chunk(kc, a.split_cpp, a.split_tab) * kBK, dx - a.pad, cy0[0] - a.pad, n_img[0]);
 #pragma unroll
                             for (int dy = 0; dy < 3; ++dy)
                                 ptx::tma_load_2d(sa + kHaloABytes + dy * C::kBBytes, &tmB, &full[s],
                                                  ((dy * 3 + dx) * skc0 + kc) * kBK, nt * BN);
+                            if (it == 0) wdm_grid_dependency_wait();
+                            ptx::tma_load_4d(sa, &tmA0, &full[s], a_chunk(kc, a.split_cpp, a.split_tab) * kBK, dx - a.pad, cy0[0] - a.pad, n_img[0]);
                         }
                         if (it == 0) tc_trace(a, 3);
                     }
@@ -787,16 +795,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             uint8_t* sa = smem + s * C::kStage;
                             uint8_t* sb = sa + MT * kABytes;
                             if (a.dbg == 1 || a.dbg == 9) {
+                                if (it == 0) wdm_grid_dependency_wait();
                                 ptx::mbar_arrive(&full[s]);
                             } else {
                             ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
+                            // a per-batch B operand is an activation (attention): it is loaded after the dependency wait too
+                            if (a.b_batched) {
+                                if (it == 0) wdm_grid_dependency_wait();
+                                ptx::tma_load_3d(sb, &tmB, &full[s], kb_lin * kBK, nt * BN, bb);
+                            } else {
+                                ptx::tma_load_2d(sb, &tmB, &full[s], kb_lin * kBK, nt * BN);
+                                if (it == 0) wdm_grid_dependency_wait();
+                            }
 #pragma unroll
                             for (int h = 0; h < MT; ++h)
                                 ptx::tma_load_4d(sa + h * kABytes, tm, &full[s], a_chunk(kc, g == 0 ? a.split_cpp : 0, a.split_tab) * kBK, cx, cy0[h] + dy - pad, n_img[h]);
-                            if (a.b_batched)
-                                ptx::tma_load_3d(sb, &tmB, &full[s], kb_lin * kBK, nt * BN, bb);
-                            else
-                                ptx::tma_load_2d(sb, &tmB, &full[s], kb_lin * kBK, nt * BN);
                             }
                             if (it == 0) tc_trace(a, 3);
                         }
@@ -871,6 +884,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
     } else if (is_epi_warp(warp)) {
         // ------------------------------------------------------------------ epilogue
+        wdm_grid_dependency_wait();
         const int ew = warp & 3, g = warp >> 2;  // TMEM lane quarter, column-half group
         const int row = ew * 32 + lane;
         uint8_t* tail = smem + C::kStages * C::kStage;
@@ -1009,7 +1023,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) tc_trace(a, 1);
-    wdm_grid_dependency_wait();  // PDL: everything above overlapped the previous kernel's tail
+    // PDL: everything above overlapped the previous kernel's tail. The dependency wait itself is per role (WDM_PDL_LATE):
+    // the producer first decodes its tile, takes the empty stage, posts the byte count and issues the WEIGHT tile (not written
+    // by the predecessor) and only then waits, right before its first activation load; the MMA issuer touches no global
+    // memory and does not wait at all; the epilogue warps wait at role entry (bias / timestep rows / residual / stores).
+    // Traced before: ~1 800 cycles between the wait and the first activation load of every launch.
+    if (!a.pdl_late) wdm_grid_dependency_wait();  // the per-role waits below then return at once
     if (threadIdx.x == 0) tc_trace(a, 2);
 
     const int num_tiles = ((a.m_tiles + 2 * MT - 1) / (2 * MT)) * a.n_tiles;  // (256 * MT)-row super-tiles
@@ -1066,16 +1085,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                             uint8_t* sa = smem + s * C::kStage;
                             uint8_t* sb = sa + MT * kABytes;
                             if (a.dbg == 1 || a.dbg == 9) {
+                                if (it == 0) wdm_grid_dependency_wait();
                                 if (leader && first) ptx::mbar_arrive(fbar);
                             } else {
                             if (leader && first) ptx::mbar_arrive_expect_tx(fbar, nb_grp * 2 * C::kStage);  // bytes of BOTH CTAs
+                            if (a.b_batched) {
+                                if (it == 0) wdm_grid_dependency_wait();
+                                ptx::tma2_load_3d(sb, &tmB, fbar, kb_lin * kBK, nrow, bb);
+                            } else {
+                                ptx::tma2_load_2d(sb, &tmB, fbar, kb_lin * kBK, nrow);
+                                if (it == 0) wdm_grid_dependency_wait();
+                            }
 #pragma unroll
                             for (int h = 0; h < MT; ++h)
                                 ptx::tma2_load_4d(sa + h * kABytes, tm, fbar, a_chunk(kc, g == 0 ? a.split_cpp : 0, a.split_tab) * kBK, cx, cy0[h] + dy - pad, n_img[h]);
-                            if (a.b_batched)
-                                ptx::tma2_load_3d(sb, &tmB, fbar, kb_lin * kBK, nrow, bb);
-                            else
-                                ptx::tma2_load_2d(sb, &tmB, fbar, kb_lin * kBK, nrow);
                             }
                             if (it == 0) tc_trace(a, 3);
                         }
@@ -1178,6 +1201,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
     } else if (is_epi_warp(warp)) {
         // ------------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        wdm_grid_dependency_wait();
         const int ew = warp & 3, g = warp >> 2;  // TMEM lane quarter, column-half group
         const int row = ew * 32 + lane;
         uint8_t* tail = smem + C::kStages * C::kStage;
@@ -1494,6 +1518,13 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     a.seg_taps[0] = p.taps, a.seg_kc[0] = (p.a_split3 == 1 ? 6 : (p.a_split3 == 2 ? 5 : 1)) * (p.C0 / kBK);
     a.split_cpp = p.a_split3 ? p.C0 / kBK : 0;
     a.split_tab = p.a_split3 == 2 ? 0x20110u : 0x201100u;  // A pieces (hi,) hi, mid, mid, hi, lo
+    {
+        static const int late = []() {
+            const char* e = getenv("WDM_PDL_LATE");  // 0: one wait for the whole CTA right after the prologue
+            return e ? atoi(e) : 1;
+        }();
+        a.pdl_late = late;
+    }
     a.seg_taps[1] = a.seg_taps[2] = 1, a.seg_kc[1] = a.seg_kc[2] = 0;
     if (p.C1) a.seg_kc[1] = p.C1 / kBK, a.nseg = 2;              // 1x1 over a concat, or the first shortcut tail
     if (p.tail_1x1 && p.C2) a.seg_kc[2] = p.C2 / kBK, a.nseg = 3;  // second shortcut tail

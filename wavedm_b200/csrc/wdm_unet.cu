@@ -1246,6 +1246,16 @@ extern "C" int wdm_gather_patches(const float* src0, int C0, const float* src1, 
     return launch_gather_patches(g, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int wdm_gather_patches_update(const float* src, int C, int c_off, int B, int h, int w, const int* patches,
+                                         int P, int R, int Cpad, void* out, int out_dtype, void* stream) {
+    (void)B;
+    if (!src || !patches || !out || C <= 0 || c_off < 0) return WDM_ERR_BAD_ARG;
+    if (out_dtype != WDM_PREC_FP32 && out_dtype != WDM_PREC_BF16) return WDM_ERR_BAD_ARG;
+    if (c_off + C > Cpad || R > h || R > w) return WDM_ERR_BAD_SHAPE;
+    return launch_gather_update(src, C, c_off, h, w, patches, P, R, Cpad, out,
+                                out_dtype == WDM_PREC_FP32 ? DT_F32 : DT_BF16, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int wdm_ddim_step(const float* eps, const int* patches, const int* img_first, int P, int B, int Cp, int R,
                              int h, int w, const float* xt, float* x0_out, float* xt_next, float at, float at_next,
                              void* stream) {

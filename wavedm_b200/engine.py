@@ -198,6 +198,22 @@ class UNetEngine:
         _lib.check(st, "wdm_gather_patches")
         return out
 
+    def gather_update(self, src: torch.Tensor, c_off: int, patches: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """Rewrites the channels [c_off, c_off + C) of a tensor ``gather`` produced from ``src`` [B, C, h, w] (the sampler's
+        x_t between DDIM steps; the conditioning channels are loop invariants of ddm_wavelet.py:467-478)."""
+        if self.wavelet_in_unet:
+            raise RuntimeError("gather_update: the wavelet_in_unet input is a DWT of the sources, gather it whole")
+        P = patches.shape[0]
+        B, C, h, w = src.shape
+        assert src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()
+        assert out.dtype == self.dtype and out.is_contiguous() and out.shape == (P, self.R, self.R, self.cin_pad)
+        with torch.cuda.device(self.device):
+            st = self.lib.wdm_gather_patches_update(src.data_ptr(), C, int(c_off), B, h, w, patches.data_ptr(), P, self.R,
+                                                    self.cin_pad, out.data_ptr(), self.prec,
+                                                    _lib.current_stream_ptr(self.device))
+        _lib.check(st, "wdm_gather_patches_update")
+        return out
+
     def forward_nhwc(self, x: torch.Tensor, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x: [P, R, R, cin_pad] engine dtype; t: fp32 device [1] or [P]. Returns eps [P, out_ch, patch, patch] fp32
         (patch = R, or 4R in wavelet_in_unet mode where the IWT is applied to the 48-channel conv_out result)."""

@@ -48,11 +48,19 @@ class _StepGraph:
         self.t = torch.zeros(1, dtype=torch.float32, device=dev)
         self.xin = torch.empty((P, eng.R, eng.R, eng.cin_pad), dtype=eng.dtype, device=dev)
         self.eps = torch.empty((P, eng.out_ch, eng.patch, eng.patch), dtype=torch.float32, device=dev)
-        srcs = [self.x_cond, self.xt] + ([self.x_other] if self.x_other is not None else [])
+        self.eng = eng
+        self.srcs = [self.x_cond, self.xt] + ([self.x_other] if self.x_other is not None else [])
+        # x_cond / x_other are loop invariants of the DDIM loop: gathered once per image batch (gather_invariants), the
+        # captured step only rewrites the channels of x_t. (wavelet_in_unet gathers DWT coefficients: whole gather per step.)
+        self.partial = not eng.wavelet_in_unet
 
         def body():
-            eng.gather(srcs, self.patches, out=self.xin)
+            if self.partial:
+                eng.gather_update(self.xt, self.x_cond.shape[1], self.patches, self.xin)
+            else:
+                eng.gather(self.srcs, self.patches, out=self.xin)
             eng.forward_nhwc(self.xin, self.t, out=self.eps)
+        self.gather_invariants()
         with torch.cuda.device(dev):    # capture on the engine's device whatever the caller's current device is
             cur = torch.cuda.current_stream(dev)
             side = torch.cuda.Stream(dev)
@@ -70,6 +78,11 @@ class _StepGraph:
         if self.x_other is not None:
             self.x_other.copy_(x_other)
         self.patches.copy_(patches)
+        self.gather_invariants()
+
+    def gather_invariants(self):
+        if self.partial:
+            self.eng.gather(self.srcs, self.patches, out=self.xin)
 
 
 class DdimSampler:
@@ -131,13 +144,19 @@ class DdimSampler:
                                       tvals, xs_hist, x0_hist, keep_history)
         xin = torch.empty((chunk, eng.R, eng.R, eng.cin_pad), dtype=eng.dtype, device=dev)
         xt = x
+        # one chunk holds every patch: the gathered tensor stays resident over the DDIM loop and steps after the first only
+        # rewrite the x_t channels (x_cond / x_other do not change: 6 instead of 256 B per pixel per step)
+        resident = P <= chunk and not eng.wavelet_in_unet
         for k, (i_t, j_t) in enumerate(zip(reversed(seq), reversed(seq_next))):
             at = float(alphas[i_t + 1])
             at_next = float(alphas[j_t + 1])
             t = tvals[k:k + 1]
             for p0 in range(0, P, chunk):
                 n = min(chunk, P - p0)
-                eng.gather([x_cond, xt] + srcs_tail, patches[p0:p0 + n], out=xin[:n])
+                if k > 0 and resident:
+                    eng.gather_update(xt, x_cond.shape[1], patches, xin)
+                else:
+                    eng.gather([x_cond, xt] + srcs_tail, patches[p0:p0 + n], out=xin[:n])
                 eng.forward_nhwc(xin[:n], t, out=eps[p0:p0 + n])
             slot = self._slot(k, S, nh)
             eng.ddim_step(eps, patches, first, xt, x0_hist[slot], xs_hist[slot], at, at_next)
