@@ -199,6 +199,21 @@ WDM_API int wdm_hfrm_forward(wdm_hfrm_t* net, const float* x, int B, int H, int 
                              size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Training-step parameter update. Replaces  utils/optimize.py:6-8  (torch.optim.Adam: betas as given,
+ * L2 weight decay, amsgrad off) followed by  models/ddm_wavelet.py:48-53  (EMAHelper.update: shadow = (1 - mu) * param +
+ * mu * shadow on the UPDATED parameters) by one launch over all parameter tensors, with the rounding points of torch's
+ * CUDA foreach implementation (csrc/wdm_optim.cu).
+ *   segs      : device int64 [T][6] = (param, grad, exp_avg, exp_avg_sq, ema_shadow, numel), fp32 contiguous tensors;
+ *   cta_first : device int32 [T + 1], prefix sums of ceil(numel / wdm_optim_chunk()); n_ctas = cta_first[T];
+ *   do_adam / do_ema select the two halves (Adam only: optimizer.step();  EMA only: ema_helper.update(); both: fused);
+ *   step      : the 1-based Adam step count of THIS update (bias corrections 1 - beta^step).
+ * ------------------------------------------------------------------------------------------------ */
+WDM_API int wdm_optim_chunk(void);
+WDM_API int wdm_adam_ema_step(const void* segs, const int* cta_first, int T, int n_ctas, int do_adam, int do_ema, double lr,
+                              double beta1, double beta2, double eps, double weight_decay, long long step, double mu,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Sampler kernels.
  * wdm_gather_patches replaces the crop + cat of  models/ddm_wavelet.py:467-478  (and the NCHW->NHWC
  * conversion of the module-level forward): out[p, y, x, c] = concat_s(src_s)[img_p, c, hi_p+y, wi_p+x],

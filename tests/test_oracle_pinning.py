@@ -211,3 +211,45 @@ def test_use_window_oracle_vs_reference_golden():
         out = O.unet_forward(sd, cfg, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]))
     ref = torch.from_numpy(g["out"])
     assert (out - ref).abs().max() <= 2e-5 * ref.abs().max()
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-2])
+def test_optim_oracle_vs_torch_adam_and_reference_ema_loop(wd):
+    """oracle/optim_oracle.py against torch.optim.Adam itself (what utils/optimize.py:7-8 constructs) and the EMA update loop
+    of ddm_wavelet.py:48-53, six steps on CPU, one tensor without a gradient. Bit-identical."""
+    from oracle.optim_oracle import AdamEmaOracle
+    g = torch.Generator().manual_seed(5)
+    params = [torch.nn.Parameter(torch.randn(n, generator=g)) for n in (1, 7, 1000, 8193)]
+    shadow = [p.data.clone() for p in params]
+    opt = torch.optim.Adam(params, lr=4e-5, weight_decay=wd, betas=(0.9, 0.999), amsgrad=False, eps=1e-8)
+    orc = AdamEmaOracle([p.data for p in params], 4e-5, (0.9, 0.999), 1e-8, wd, mu=0.9999)
+    for it in range(6):
+        grads = [torch.randn(p.shape, generator=g) * 10.0 ** (it - 3) for p in params]
+        grads[1] = None
+        for p, gr in zip(params, grads):
+            p.grad = gr
+        opt.step()
+        for i, p in enumerate(params):
+            shadow[i] = (1. - 0.9999) * p.data + 0.9999 * shadow[i]
+        orc.step(grads)
+    for i, p in enumerate(params):
+        assert torch.equal(p.data, orc.p[i]), i
+        assert torch.equal(shadow[i], orc.shadow[i]), i
+        if i != 1:
+            assert torch.equal(opt.state[p]["exp_avg"], orc.m[i]) and torch.equal(opt.state[p]["exp_avg_sq"], orc.v[i])
+
+
+def test_get_optimizer_on_cpu_is_torch_adam_and_fused_adam_refuses_cpu_parameters():
+    """utils/optimize.py:5-14 factory: a model on the CPU gets torch.optim.Adam (the reference's object); the fused CUDA
+    optimizer never steps CPU tensors through some other implementation."""
+    from types import SimpleNamespace as NS
+    from wavedm_b200 import optimize
+    cfg = NS(optim=NS(optimizer="Adam", lr=4e-5, weight_decay=0.0, amsgrad=False, eps=1e-8))
+    lin = torch.nn.Linear(3, 2)
+    opt = optimize.get_optimizer(cfg, lin.parameters())
+    assert type(opt) is torch.optim.Adam
+    lin(torch.ones(1, 3)).sum().backward()
+    with pytest.raises(RuntimeError):
+        optimize.FusedAdam(lin.parameters(), lr=1e-3).step()
+    with pytest.raises(NotImplementedError):
+        optimize.FusedAdam(lin.parameters(), lr=1e-3, amsgrad=True)

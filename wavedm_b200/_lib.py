@@ -119,6 +119,9 @@ def load() -> ctypes.CDLL:
         "wdm_hfrm_destroy": (None, [c_void_p]),
         "wdm_hfrm_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
         "wdm_hfrm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+        "wdm_optim_chunk": (c_int, []),
+        "wdm_adam_ema_step": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                      ctypes.c_double, c_longlong, ctypes.c_double, c_void_p]),
         "wdm_gather_patches": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                        c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
         "wdm_gather_patches_update": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,

@@ -53,9 +53,30 @@ class EMAHelper(object):
                 self.shadow[name] = param.data.clone()
 
     def update(self, module):
-        for name, param in self._unwrap(module).named_parameters():
-            if param.requires_grad:
-                self.shadow[name].data = (1. - self.mu) * param.data + self.mu * self.shadow[name].data
+        """ddm_wavelet.py:48-53. CUDA parameters: one launch of ``wdm_adam_ema_step`` (EMA half) over all tensors, in place
+        -- or nothing at all when the attached ``FusedAdam.step()`` already updated the shadow in its own launch."""
+        if getattr(self, "_fused_update_done", False):
+            self._fused_update_done = False
+            return
+        named = [(n, p) for n, p in self._unwrap(module).named_parameters() if p.requires_grad]
+        if named and all(p.is_cuda for _, p in named):
+            from .optimize import SegmentTable
+            dev = named[0][1].device
+            rows = []
+            for n, p in named:
+                sh = self.shadow[n]
+                if sh.dtype != torch.float32 or p.dtype != torch.float32 or not sh.is_contiguous() or not p.is_contiguous() \
+                        or sh.device != dev or p.device != dev:
+                    raise TypeError("EMAHelper.update: dense contiguous float32 parameters / shadows on one device expected")
+                if p.numel():
+                    rows.append((p.data_ptr(), 0, 0, 0, sh.data_ptr(), p.numel()))
+            tab = self.__dict__.get("_table")
+            if tab is None or tab.device != dev:
+                tab = self._table = SegmentTable(dev)
+            tab.update(rows).launch(False, True, mu=self.mu)
+            return
+        for name, param in named:
+            self.shadow[name].data = (1. - self.mu) * param.data + self.mu * self.shadow[name].data
 
     def ema(self, module):
         """ddm_wavelet.py:63-66. Written through ``param.copy_`` under no_grad (not ``param.data``) so the tensors' version
@@ -158,6 +179,8 @@ class DenoisingDiffusion_Wavelet(object):
         self.ema_helper = EMAHelper()
         self.ema_helper.register(self.model)
         self.optimizer = woptimize.get_optimizer(self.config, self.model.parameters())
+        if hasattr(self.optimizer, "attach_ema"):   # CUDA: Adam + EMA shadow update in one launch per training step
+            self.optimizer.attach_ema(self.ema_helper, self.model)
         self.start_epoch, self.step = 0, 0
 
         print("my local rank", self.args.local_rank)
