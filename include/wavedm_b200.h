@@ -299,10 +299,17 @@ typedef struct wdm_gemm_params {
     int a_split3;
     const void* B3;
     const void* B3m;
+    /* tensor-core path only, small problems (few output tiles, deep K: single-image latency): ksplit = S > 1 runs the K loop
+     * on S CTAs per output tile, raw fp32 partial results go to ksplit_scratch ([S][M][N] floats, 16-byte aligned) and a
+     * second launch reduces them in split order and applies alpha / bias / temb / residual / stats_out. S must not exceed
+     * wdm_gemm_ksplit_plan(p) (1 = not applicable: the plain launch). 0 / 1: off. */
+    int ksplit;
+    void* ksplit_scratch;
 } wdm_gemm_params;
 #define WDM_GEMM_IMPL_SIMT 0
 #define WDM_GEMM_IMPL_TC 1
 WDM_API int wdm_gemm(const wdm_gemm_params* p, int impl, void* stream);
+WDM_API int wdm_gemm_ksplit_plan(const wdm_gemm_params* p);
 /* tc32 helpers (unit tests; the executor calls the same kernels): split an fp32 matrix (two channel-concatenated sources)
  * into [rows][3*(C0+C1)] bf16 pieces / a packed fp32 weight matrix [N][taps][C] into [N][taps][6][C] bf16. */
 WDM_API int wdm_split3_act(const float* src0, int C0, const float* src1, int C1, long long rows, void* out, void* stream);

@@ -33,10 +33,11 @@ class GemmParams(ctypes.Structure):
                                                                                 ("src2", ctypes.c_void_p), ("C2", ctypes.c_int), ("ld2", ctypes.c_int),
                                                                                 ("fuse_softmax", ctypes.c_int), ("softmax_seg", ctypes.c_int), ("out_nchw_valid", ctypes.c_int),
                                                                                 ("row_scale_out", ctypes.c_void_p), ("row_scale", ctypes.c_void_p),
-                                                                                ("a_split3", ctypes.c_int), ("B3", ctypes.c_void_p), ("B3m", ctypes.c_void_p)]
+                                                                                ("a_split3", ctypes.c_int), ("B3", ctypes.c_void_p), ("B3m", ctypes.c_void_p),
+                                                                                ("ksplit", ctypes.c_int), ("ksplit_scratch", ctypes.c_void_p)]
 
 
-def run_conv(x, x2, w, bias, stride, ups, temb, residual, dtype, impl, want_stats=False):
+def run_conv(x, x2, w, bias, stride, ups, temb, residual, dtype, impl, want_stats=False, ksplit=None):
     """x, x2: NCHW fp32 torch (cpu); w OIHW. Runs the C-ABI gemm on NHWC tensors, returns NCHW fp32."""
     lib = _lib.load()
     td = torch.float32 if dtype == 0 else torch.bfloat16
@@ -77,6 +78,13 @@ def run_conv(x, x2, w, bias, stride, ups, temb, residual, dtype, impl, want_stat
     if want_stats:
         stats = torch.full((p.M // 32, Cout // 4, 2), float("nan"), device=DEV)
         p.stats_out = stats.data_ptr()
+    if ksplit is not None:   # split-K: "plan" = what the engine would use, or an explicit factor
+        plan = lib.wdm_gemm_ksplit_plan(ctypes.byref(p))
+        S = plan if ksplit == "plan" else int(ksplit)
+        assert 2 <= S <= plan, (S, plan)
+        scratch = torch.full((S, p.M, p.N), float("nan"), device=DEV)
+        keep.append(scratch)
+        p.ksplit, p.ksplit_scratch = S, scratch.data_ptr()
     st = lib.wdm_gemm(ctypes.byref(p), impl, torch.cuda.current_stream().cuda_stream)
     _lib.check(st, "wdm_gemm")
     torch.cuda.synchronize()
@@ -173,6 +181,44 @@ def test_gemm_tc_conv_cases(case):
     # and it agrees with the CUDA-core kernel on the same data
     outs = run_conv(x, x2, w, bias, stride, ups, temb, res, 1, _lib.WDM_GEMM_IMPL_SIMT)
     assert (out - outs).abs().max().item() <= 1e-2 * scale
+
+
+SPLITK_CASES = [
+    # P, C0, C1, Cout, H, k, stride, ups, temb_rows, residual, ksplit
+    (1, 1536, 0, 768, 8, 3, 1, 0, 1, True, "plan"),    # the deepest P = 1 shape: M = 64 (half a tile), 216 k-blocks
+    (1, 512, 0, 512, 16, 3, 1, 0, 1, False, "plan"),   # 16x16 level, M = 256
+    (2, 768, 0, 768, 8, 3, 1, 0, 2, True, "plan"),     # two patches in one tile, per-patch temb rows
+    (1, 1024, 0, 512, 16, 3, 1, 0, 0, True, 2),        # smallest factor
+    (1, 768, 0, 768, 8, 3, 1, 0, 0, False, 5),         # 108 k-blocks over 5 splits: uneven ranges
+    (1, 512, 0, 256, 16, 3, 2, 0, 0, False, "plan"),   # stride-2 (out 8x8), M = 64
+]
+
+
+@pytest.mark.parametrize("case", SPLITK_CASES)
+def test_gemm_tc_splitk_cases(case):
+    """Split-K form of the tcgen05 contraction (single-image latency path: few output tiles, deep K): the same result as the
+    one-CTA-per-tile launch up to fp32 summation order, GroupNorm side-car included."""
+    P, C0, C1, Cout, H, k, stride, ups, trows, has_res, ks = case
+    g = torch.Generator().manual_seed(31)
+    rb = lambda t: t.bfloat16().float()
+    x = rb(torch.randn(P, C0, H, H, generator=g))
+    w = rb(torch.randn(Cout, C0, k, k, generator=g) / (k * C0 ** 0.5))
+    bias = torch.randn(Cout, generator=g)
+    temb = torch.randn(trows, Cout, generator=g) if trows else None
+    Ho = H // 2 if stride == 2 else H
+    res = rb(torch.randn(P, Cout, Ho, Ho, generator=g)) if has_res else None
+    ref = ref_conv(x, None, w, bias, stride, ups, temb, res)
+    lib = _lib.load()
+    n0 = lib.wdm_launch_counter()
+    out, stats = run_conv(x, None, w, bias, stride, ups, temb, res, 1, _lib.WDM_GEMM_IMPL_TC, want_stats=True, ksplit=ks)
+    assert lib.wdm_launch_counter() - n0 == 2          # contraction + reduce / epilogue
+    plain, stats_plain = run_conv(x, None, w, bias, stride, ups, temb, res, 1, _lib.WDM_GEMM_IMPL_TC, want_stats=True)
+    scale = max(1.0, ref.abs().max().item())
+    assert (out - ref).abs().max().item() <= 6e-3 * scale
+    assert (out - plain).abs().max().item() <= 2 ** -7 * scale          # one bf16 ulp where the fp32 sums round differently
+    assert float((out != plain).float().mean()) < 0.02
+    assert not torch.isnan(stats).any()
+    assert (stats - stats_plain).abs().max().item() <= 1e-4 * max(1.0, stats_plain.abs().max().item())
 
 
 @pytest.mark.parametrize("case", [(2, 256, 128, 128, 16), (2, 768, 768, 512, 8), (3, 128, 256, 0, 32), (2, 512, 512, 256, 16)])

@@ -132,6 +132,7 @@ def load() -> ctypes.CDLL:
         "wdm_ddim_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_float, c_float, c_void_p]),
         "wdm_gemm": (c_int, [c_void_p, c_int, c_void_p]),
+        "wdm_gemm_ksplit_plan": (c_int, [c_void_p]),
         "wdm_groupnorm_scratch_bytes": (c_size_t, [c_int]),
         "wdm_groupnorm_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p,
                                        c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -30,6 +30,7 @@ int launch_gemm_simt(const GemmParams& p, cudaStream_t stream);
 // tcgen05 / TMA path (wdm_gemm_tc.cu); returns WDM_ERR_UNSUPPORTED for shapes it does not tile.
 bool gemm_tc_supported(const GemmParams& p);
 int launch_gemm_tc(const GemmParams& p, cudaStream_t stream);
+int gemm_tc_ksplit_plan(const GemmParams& p);  // split-K factor worth using for p (1 = none), see wdm_gemm_params::ksplit
 
 // conv_out (models/unet.py:303-307, Cout <= 4): NHWC in -> NCHW fp32 out [P, Cout, H, W].
 int launch_conv_small_cout(const void* src, int dtype, int P, int H, int W, int C, const float* w /*[Cout][9][C]*/,

@@ -78,6 +78,10 @@ struct TcArgs {
     int split_cpp;             // tc32: 64-channel chunks per bf16 piece of segment 0 (0 = plain operands), see a_chunk()
     uint32_t split_tab;        // tc32: A piece of product pr in nibble pr
     int pdl_late;              // the dependency wait moves into the roles (see the kernels)
+    int ksplit;                // > 1: split-K (1-CTA non-halo kernel only): virtual tile = (split, tile), split s walks k-blocks
+                               // [s*kb/S, (s+1)*kb/S) and stores its raw fp32 accumulator to out + s*ksplit_stride (no epilogue
+                               // terms); splitk_finish_kernel reduces the slabs and applies the epilogue
+    long long ksplit_stride;   // fp32 elements between two slabs
 };
 
 // tc32 (fp32 emulated by a 3-way bf16 split, GemmParams::a_split3): the K loop of a tap walks SIX products
@@ -232,7 +236,7 @@ __device__ __forceinline__ void epi_stage(const TcArgs& a, int mt0, int nt, int 
 template <int BN, int MT>
 __device__ __forceinline__ void epi_rows(const TcArgs& a, const CUtensorMap* tmO, uint32_t tacc, int mt0, int nt, int ew, int g,
                                          int lane, int row, const EpiSmem& es, uint4 (&r0)[4], uint4 (&r1)[4],
-                                         const float (&rsc)[MT], bool tr = false) {
+                                         const float (&rsc)[MT], bool tr = false, long long out_off = 0) {
     constexpr int kCh = BN / 32, kCh2 = (kCh + 1) / 2, kF = MT * kCh2, kW = kCh2 * 32;
     const float* sb = es.sb;
     const bool tma = a.epi_tma != 0;
@@ -301,7 +305,7 @@ __device__ __forceinline__ void epi_rows(const TcArgs& a, const CUtensorMap* tmO
                         v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
                     }
                 }
-                float* op = reinterpret_cast<float*>(a.out) + e.orow * a.ldo + n;
+                float* op = reinterpret_cast<float*>(a.out) + out_off + e.orow * a.ldo + n;  // out_off: split-K slab
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -645,6 +649,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int num_tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;  // super-tiles of MT m-tiles
     int kblocks = 0;
     for (int g = 0; g < a.nseg; ++g) kblocks += a.seg_taps[g] * a.seg_kc[g];
+    const int ks = (!HALO && !SWAP && a.ksplit > 1) ? a.ksplit : 1;  // split-K (see TcArgs::ksplit)
+    const int vtiles = num_tiles * ks;
 
     if (HALO && warp == kWarpTma) {
         // ------------------------------------------------------------------ TMA producer, halo macro-stages
@@ -768,7 +774,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     } else if (warp == kWarpTma) {
         // ------------------------------------------------------------------ TMA producer
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int vt = blockIdx.x; vt < vtiles; vt += gridDim.x) {
+            const int sp = vt / num_tiles, tile = vt - sp * num_tiles;
+            const int kb0 = (int)((long long)sp * kblocks / ks), kb1 = (int)((long long)(sp + 1) * kblocks / ks);
             const int st = tile / a.n_tiles, nt = tile - st * a.n_tiles;
             int n_img[MT], cy0[MT];
 #pragma unroll
@@ -788,7 +796,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     int dy = staps == 9 ? tap / 3 : 0, dx = staps == 9 ? tap % 3 : 0;
                     if (a.subpix) dy = (bb >> 1) - 1 + (tap >> 1), dx = (bb & 1) - 1 + (tap & 1);  // bb = output phase
                     const int cx = dx - pad;
-                    for (int kc = 0; kc < skc; ++kc, ++it, ++kb_lin) {
+                    for (int kc = 0; kc < skc; ++kc, ++kb_lin) {
+                        if (kb_lin < kb0 || kb_lin >= kb1) continue;  // split-K: another CTA's k-blocks
                         const uint32_t s = it % C::kStages, ph = (it / C::kStages) & 1;
                         ptx::mbar_wait(&empty[s], ph ^ 1);
                         if (lane == 0) {
@@ -814,6 +823,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             if (it == 0) tc_trace(a, 3);
                         }
                         __syncwarp();
+                        ++it;
                     }
                 }
             }
@@ -823,7 +833,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         constexpr uint32_t idesc = SWAP ? make_idesc(BN, MT * kBM) : make_idesc(kBM, BN);
         static_assert(!SWAP || (BN == 128 && MT == 2), "swap-AB: 128 output channels x 256 pixels");
         uint32_t it = 0, tl = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+        for (int vt = blockIdx.x; vt < vtiles; vt += gridDim.x, ++tl) {
+            const int sp = vt / num_tiles;
+            const int kb0 = (int)((long long)sp * kblocks / ks), kb1 = (int)((long long)(sp + 1) * kblocks / ks);
             const uint32_t as = tl % C::kBufs, aph = (tl / C::kBufs) & 1;
             ptx::mbar_wait(&tempty[as], aph ^ 1);
             ptx::tc_fence_after();
@@ -831,8 +843,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             // Two k-blocks per issue group: the barrier wait / fence / commit overhead (~240 cycles) is paid once per
             // 8*MT MMAs instead of once per 4*MT (the single issuing thread is the scarce resource: a tcgen05.mma costs
             // ~76 issue cycles, see tools/mma_rate.cu).
-            for (int kb = 0; kb < kblocks;) {
-                const int nb = (kblocks - kb) >= 2 ? 2 : 1;
+            for (int kb = kb0; kb < kb1;) {
+                const int nb = (kb1 - kb) >= 2 ? 2 : 1;
                 uint32_t sidx[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -856,14 +868,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                 const uint64_t dx = make_smem_desc(sa);
 #pragma unroll
                                 for (int k = 0; k < kBK / 16; ++k)
-                                    ptx::umma_f16_ss(d_tmem, db + 2 * k, dx + 2 * k, idesc, ((kb + j) | k) ? 1u : 0u);
+                                    ptx::umma_f16_ss(d_tmem, db + 2 * k, dx + 2 * k, idesc, ((kb + j - kb0) | k) ? 1u : 0u);
                             } else {
 #pragma unroll
                                 for (int k = 0; k < kBK / 16; ++k) {
 #pragma unroll
                                     for (int h = 0; h < MT; ++h)
                                         ptx::umma_f16_ss(d_tmem + h * BN, make_smem_desc(sa + h * kABytes) + 2 * k, db + 2 * k,
-                                                         idesc, ((kb + j) | k) ? 1u : 0u);
+                                                         idesc, ((kb + j - kb0) | k) ? 1u : 0u);
                                 }
                             }
                         }
@@ -872,7 +884,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     for (int j = 0; j < 2; ++j)
                         if (j < nb) ptx::umma_commit(&empty[sidx[j]]);
                     if (tl == 1 && kb >= 8 && kb < 16) tc_trace(a, 25 + (kb - 8));  // group issued + committed
-                    if (kb + nb == kblocks) {
+                    if (kb + nb == kb1) {
                         ptx::umma_commit(&tfull[as]);
                         if (tl < 2) tc_trace(a, 5 + tl);
                     }
@@ -892,7 +904,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         es.sb = reinterpret_cast<float*>(tail + kTailBars) + (g * 4 + ew) * (MT * (BN / 2));
         es.ebuf = tail + tail_epi_off(BN, MT) + (g * 4 + ew) * kEpiChunkBytes;
         uint32_t tl = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+        for (int vt = blockIdx.x; vt < vtiles; vt += gridDim.x, ++tl) {
+            const int sp = vt / num_tiles, tile = vt - sp * num_tiles;
             const int st = tile / a.n_tiles, nt = tile - st * a.n_tiles;
             const uint32_t as = tl % C::kBufs, aph = (tl / C::kBufs) & 1;
             if (a.residual && g == 0) {
@@ -930,7 +943,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 epi_rows_swap(a, tacc, st * MT, nt, ew, g, lane);
             } else {
                 epi_rows<BN, MT>(a, &tmO, tacc, st * MT, nt, ew, g, lane, row, es, r0, r1, rsc,
-                                 a.trace && threadIdx.x == 0 && tl == 0);
+                                 a.trace && threadIdx.x == 0 && tl == 0, (long long)sp * a.ksplit_stride);
             }
             if (threadIdx.x == 0 && tl < 2) tc_trace(a, 8 + 2 * tl);
             ptx::tc_fence_before();
@@ -1306,7 +1319,7 @@ int launch_bn(const CUtensorMap& A0, const CUtensorMap& A1, const CUtensorMap& A
     using C = Cfg<BN, MT, HALO>;
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MT, SWAP, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
-    const int tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles;
+    const int tiles = ((a.m_tiles + MT - 1) / MT) * a.n_tiles * (!SWAP && !HALO && a.ksplit > 1 ? a.ksplit : 1);
     const int grid = tiles < num_sms_tc() ? tiles : num_sms_tc();
     e = wdm_launch_pdl(gemm_tc_kernel<BN, MT, SWAP, HALO>, dim3(grid), dim3(kThreads), C::kSmem, s, A0, A1, A2, B, O, a);
     if (e != cudaSuccess) return wdm_cuda_error((int)e);
@@ -1398,7 +1411,7 @@ bool gemm_tc_supported(const GemmParams& p) {
     return true;
 }
 
-int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
+static int launch_gemm_tc_impl(const GemmParams& p, int ksplit, cudaStream_t s) {
     if (!gemm_tc_supported(p)) return WDM_ERR_UNSUPPORTED;
     {
         static const int forced = []() {
@@ -1416,6 +1429,17 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     const int HWout = Hm * Wm;
     const int npatch = p.a_shared ? 1 : (subpix ? p.M / (4 * HWout) : (p.M + HWout - 1) / HWout);
     int BN = pick_bn(p.N);
+    // Small problems (single-image latency: P = 1 gives 1-32 m-tiles): a launch that would occupy a handful of SMs with
+    // 128/256-wide tiles walks its K loop at the MMA rate of those few SMs (216 k-blocks x 0.34 us at 8x8). 64-wide tiles
+    // put 2-4x as many SMs on the same K depth; the loop then runs at the operand-fill rate of a k-block instead.
+    static const int small_bn = []() {
+        const char* e = getenv("WDM_TC_SMALL_BN");
+        return e ? atoi(e) : 1;
+    }();
+    if (small_bn && BN > 64 && !subpix && !p.b_batch_stride && !p.a_shared && !p.fuse_softmax && !p.a_split3 &&
+        (long long)((p.M + kBM - 1) / kBM) * (p.N / BN) * 8 <= num_sms_tc())
+        BN = 64;
+    if (ksplit > 1) BN = 64;  // split-K: 1-CTA tiles, as many weight streams as possible (gemm_tc_ksplit_plan checked the shape)
     static const int pair_enabled = []() {
         const char* e = getenv("WDM_TC_PAIR");
         return e ? atoi(e) : 1;
@@ -1433,8 +1457,8 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     }();
     const bool pair128x2 = pair_enabled && pair128x2_enabled && BN == 128 && !p.b_batch_stride && !subpix && !p.a_shared &&
                            (p.M + kBM - 1) / kBM >= 4 * (num_sms_tc() / 2);
-    const bool use_pair = pair128x2 || (pair_enabled && (BN == 256 || (BN == 128 && pair128)) &&
-                                        ((!p.b_batch_stride && !subpix) || tiles_per_batch_h % 2 == 0));
+    const bool use_pair = ksplit <= 1 && (pair128x2 || (pair_enabled && (BN == 256 || (BN == 128 && pair128)) &&
+                                                        ((!p.b_batch_stride && !subpix) || tiles_per_batch_h % 2 == 0)));
     bool pair192 = false;
     static const int pair192_enabled = []() {
         const char* e = getenv("WDM_TC_PAIR192");
@@ -1456,7 +1480,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         return e ? atoi(e) : 1;
     }();
     const int m_tiles_all = (p.M + kBM - 1) / kBM;
-    const bool use_halo = halo_enabled && !use_pair && BN == 128 && p.taps == 9 && p.stride == 1 && !subpix &&
+    const bool use_halo = ksplit <= 1 && halo_enabled && !use_pair && BN == 128 && p.taps == 9 && p.stride == 1 && !subpix &&
                           !p.b_batch_stride && !p.a_shared && !p.fuse_softmax && g.Nb == 1 && (HWout % (2 * kBM)) == 0 &&
                           (2 * g.Hb + 2) * g.Wb * 128 <= kHaloABytes && (!p.C1 || p.tail_1x1) && g_force_mt != 1 &&
                           pick_mt(m_tiles_all, p.N / BN, BN, true) == 2;
@@ -1525,6 +1549,8 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         }();
         a.pdl_late = late;
     }
+    a.ksplit = ksplit > 1 ? ksplit : 1;
+    a.ksplit_stride = (long long)p.M * p.ldo;
     a.seg_taps[1] = a.seg_taps[2] = 1, a.seg_kc[1] = a.seg_kc[2] = 0;
     if (p.C1) a.seg_kc[1] = p.C1 / kBK, a.nseg = 2;              // 1x1 over a concat, or the first shortcut tail
     if (p.tail_1x1 && p.C2) a.seg_kc[2] = p.C2 / kBK, a.nseg = 3;  // second shortcut tail
@@ -1639,7 +1665,7 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
         return pair192 ? launch_pair<192>(A0, A1, A2, B, O, a, s) : launch_pair<256>(A0, A1, A2, B, O, a, s);
     }
     const bool allow2 = !a.b_batched || (a.tiles_per_batch % 2 == 0);
-    const int MT = g_force_mt ? (g_force_mt == 2 && allow2 && BN != 256 ? 2 : 1) : pick_mt(a.m_tiles, a.n_tiles, BN, allow2);
+    const int MT = ksplit > 1 ? 1 : (g_force_mt ? (g_force_mt == 2 && allow2 && BN != 256 ? 2 : 1) : pick_mt(a.m_tiles, a.n_tiles, BN, allow2));
     if (BN == 256) return launch_bn<256, 1>(A0, A1, A2, B, O, a, s);
     if (use_halo) return launch_bn<128, 2, false, true>(A0, A1, A2, B, O, a, s);
     if (BN == 128 && MT == 2) {
@@ -1654,6 +1680,123 @@ int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
     }
     if (BN == 128) return MT == 2 ? launch_bn<128, 2>(A0, A1, A2, B, O, a, s) : launch_bn<128, 1>(A0, A1, A2, B, O, a, s);
     return MT == 2 ? launch_bn<64, 2>(A0, A1, A2, B, O, a, s) : launch_bn<64, 1>(A0, A1, A2, B, O, a, s);
+}
+
+// ------------------------------------------------------------------------------------------------ split-K (small problems)
+// Single-image latency (P = 1..4): a 3x3 convolution at 16x16 / 8x8 has 1-4 m-tiles and a K loop of 72-216 k-blocks; a CTA
+// streams its weight slice at ~70 GB/s (bytes in flight / latency), so a launch on 2-12 SMs takes 35-78 us for 7-21 MB of
+// weights while 130+ SMs idle (profiles/r02_p1_spans.txt). Split-K puts (tiles x S) CTAs on the problem: split s accumulates
+// k-blocks [s*kb/S, (s+1)*kb/S) and stores its raw fp32 accumulator to slab s of a scratch tensor (L2-resident: <= 10 MB);
+// splitk_finish_kernel adds the slabs in split order (deterministic) and applies the epilogue of epi_rows -- alpha, bias +
+// timestep row, residual, bf16 rounding, GroupNorm side-car with the same summation tree.
+int gemm_tc_ksplit_plan(const GemmParams& p) {
+    static const int enabled = []() {
+        const char* e = getenv("WDM_TC_SPLITK");
+        return e ? atoi(e) : 1;
+    }();
+    if (!enabled || !gemm_tc_supported(p)) return 1;
+    if (p.ups || p.b_batch_stride || p.a_shared || p.fuse_softmax || p.a_split3 || p.out_nchw_valid || p.row_scale ||
+        p.row_scale_out || p.out_dtype != DT_BF16 || (p.N % 64) || (p.M % 32) || p.ldo != p.N)
+        return 1;
+    if (p.residual && ((p.ldr % 8) || !wdm_aligned(p.residual, 16))) return 1;
+    if (p.temb && p.temb_rows > 1 && ((p.Hout * p.Wout) % 32)) return 1;
+    const int kf = 1;
+    const int kblocks = p.tail_1x1 ? p.K / kBK : p.taps * kf * (p.C0 + p.C1) / kBK;
+    const long long tiles = (long long)((p.M + kBM - 1) / kBM) * (p.N / 64);
+    if (tiles * 2 > num_sms_tc() || kblocks < 32) return 1;   // enough CTAs already, or nothing to split
+    long long S = num_sms_tc() / tiles;
+    if (S > kblocks / 8) S = kblocks / 8;
+    if (S > 32) S = 32;
+    return S >= 2 ? (int)S : 1;
+}
+
+// One CTA per (32-row group, 32-column chunk); thread = (row, 4-column block): every slab load is a fully used 128-byte line
+// per 8 lanes and all S loads of a thread are independent (the first version had a thread walk a whole row chunk of every
+// slab: 6-32 CTAs, 10-21 us of exposed L2 latency per launch -- longer than the split contraction itself).
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ part, int S, long long slab, int M, int N,
+                                                            float alpha, const float* __restrict__ bias,
+                                                            const float* __restrict__ temb, int temb_rows, int temb_ld, int HW,
+                                                            const __nv_bfloat16* __restrict__ residual, int ldr,
+                                                            __nv_bfloat16* __restrict__ out, int ldo, float* __restrict__ stats) {
+    __shared__ float red[2][8][33];  // [sum | sum of squares][4-column block][row], padded
+    const int row = threadIdx.x >> 3, blk = threadIdx.x & 7;
+    const int rg = blockIdx.x, n = blockIdx.y * 32 + blk * 4;
+    const long long m = (long long)rg * 32 + row;
+    const bool valid = m < M;
+    // epilogue operands do not depend on the contraction: requested before the dependency wait
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid && bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+    wdm_grid_dependency_wait();
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
+        if (temb) {  // written by the timestep MLP of this forward: after the wait
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(temb + (temb_rows > 1 ? (m / HW) * temb_ld : 0) + n));
+            b4.x += t4.x, b4.y += t4.y, b4.z += t4.z, b4.w += t4.w;
+        }
+        uint2 r2 = make_uint2(0u, 0u);
+        if (residual) r2 = __ldg(reinterpret_cast<const uint2*>(residual + m * ldr + n));
+        const float* pp = part + m * N + n;
+        int s_ = 0;
+        for (; s_ + 4 <= S; s_ += 4) {  // slabs are added in split order (deterministic)
+            float4 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const float4*>(pp + (s_ + u) * slab);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v.x += t[u].x, v.y += t[u].y, v.z += t[u].z, v.w += t[u].w;
+        }
+        for (; s_ < S; ++s_) {
+            const float4 t = *reinterpret_cast<const float4*>(pp + s_ * slab);
+            v.x += t.x, v.y += t.y, v.z += t.z, v.w += t.w;
+        }
+        if (alpha != 1.f) v.x *= alpha, v.y *= alpha, v.z *= alpha, v.w *= alpha;
+        if (bias || temb) v.x += b4.x, v.y += b4.y, v.z += b4.z, v.w += b4.w;
+        if (residual) {
+            v.x += __uint_as_float(r2.x << 16), v.y += __uint_as_float(r2.x & 0xffff0000u);
+            v.z += __uint_as_float(r2.y << 16), v.w += __uint_as_float(r2.y & 0xffff0000u);
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(out + m * ldo + n) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+    if (stats) {
+        // per 4-column block (sum, sum of squares) of the fp32 values, then the 32 rows in the butterfly order of epi_rows
+        // (x[i] += x[i + o], o = 16, 8, 4, 2, 1): the same fp32 result for the same values
+        red[0][blk][row] = valid ? (v.x + v.y) + (v.z + v.w) : 0.f;
+        red[1][blk][row] = valid ? fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w) : 0.f;
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            const int b = threadIdx.x >> 1, which = threadIdx.x & 1;
+            float x[32];
+#pragma unroll
+            for (int i_ = 0; i_ < 32; ++i_) x[i_] = red[which][b][i_];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int i_ = 0; i_ < o; ++i_) x[i_] += x[i_ + o];
+            }
+            if ((long long)rg * 32 < M) stats[((long long)rg * (N >> 2) + (n >> 2) - blk + b) * 2 + which] = x[0];
+        }
+    }
+}
+
+int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
+    if (p.ksplit <= 1) return launch_gemm_tc_impl(p, 1, s);
+    if (!p.ksplit_scratch || p.ksplit > gemm_tc_ksplit_plan(p) || !wdm_aligned(p.ksplit_scratch, 16)) return WDM_ERR_BAD_ARG;
+    GemmParams q = p;
+    q.out = p.ksplit_scratch, q.out_dtype = DT_F32, q.ldo = p.N;
+    q.alpha = 1.f, q.bias = nullptr, q.temb = nullptr, q.temb_rows = 0, q.residual = nullptr, q.stats_out = nullptr;
+    q.ksplit = 0, q.ksplit_scratch = nullptr;
+    if (!gemm_tc_supported(q)) return WDM_ERR_BAD_ARG;
+    int st = launch_gemm_tc_impl(q, p.ksplit, s);
+    if (st != WDM_OK) return st;
+    dim3 grid((unsigned)((p.M + 31) / 32), (unsigned)(p.N / 32));
+    cudaError_t e = wdm_launch_pdl(splitk_finish_kernel, grid, dim3(256), (size_t)0, s,
+                                   reinterpret_cast<const float*>(p.ksplit_scratch), p.ksplit, (long long)p.M * p.N, p.M, p.N,
+                                   p.alpha, p.bias, p.temb, p.temb_rows, p.temb_ld, p.Hout * p.Wout,
+                                   reinterpret_cast<const __nv_bfloat16*>(p.residual), p.ldr,
+                                   reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, p.stats_out);
+    if (e != cudaSuccess) return wdm_cuda_error((int)e);
+    return wdm_launch_status();
 }
 
 }  // namespace wdm

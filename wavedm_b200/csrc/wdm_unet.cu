@@ -591,6 +591,22 @@ bool run_gemm_tc32(Ctx& c, const GemmParams& p) {
 
 int run_gemm(Ctx& c, const GemmParams& p) {
     if (run_gemm_tc32(c, p)) return c.st;
+    if (will_use_tc(c, p)) {
+        // few output tiles under a deep K loop (single-image latency): split-K over otherwise idle SMs (wdm_gemm_tc.cu)
+        const int S = gemm_tc_ksplit_plan(p);
+        if (S > 1) {
+            GemmParams q = p;
+            q.ksplit = S;
+            q.ksplit_scratch = c.ar->alloc((size_t)S * p.M * p.N * sizeof(float));
+            if (c.ar->failed) {
+                c.fail(WDM_ERR_WORKSPACE);
+                return c.st;
+            }
+            run_gemm_impl(c, q);
+            c.ar->free(q.ksplit_scratch);
+            return c.st;
+        }
+    }
     return run_gemm_impl(c, p);
 }
 
@@ -1276,6 +1292,8 @@ extern "C" int wdm_gemm(const wdm_gemm_params* p, int impl, void* stream) {
     }
     return WDM_ERR_BAD_ARG;
 }
+
+extern "C" int wdm_gemm_ksplit_plan(const wdm_gemm_params* p) { return p ? gemm_tc_ksplit_plan(*p) : 1; }
 
 extern "C" size_t wdm_groupnorm_scratch_bytes(int P) { return gn_stats_bytes(P); }
 
