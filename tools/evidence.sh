@@ -69,5 +69,9 @@ timeout 300 python tools/bench_hfrm.py > $O/${TAG}_bench_hfrm.txt 2>&1
 # 6. per-step GPU timeline of the sampler + single-image latency
 timeout 300 python tools/sampler_timeline.py 2>&1 | tail -6 > $O/${TAG}_sampler_timeline.txt
 timeout 300 python tools/latency_small.py > $O/${TAG}_latency_small.txt 2>&1
+# 7. single-image call (P = 1): per-shape event table with split-K, and the training-step update kernel
+timeout 300 python tools/profile_unet.py --patches 1 --iters 5 --time --spans > $O/${TAG}_p1_spans_splitk.txt 2>&1
+WDM_TC_SPLITK=0 timeout 300 python tools/latency_small.py > $O/${TAG}_latency_small_nosplit.txt 2>&1
+timeout 600 python tools/bench_train_step.py --json $O/${TAG}_train_step.json > $O/${TAG}_train_step.txt 2>&1
 du -sh $O
 ls -la $O | grep ${TAG}_ | head -40
