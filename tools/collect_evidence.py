@@ -1,4 +1,4 @@
-"""Copies the outputs of tools/gpu_call19.sh (gpurun_out/f_* and gpurun_out/r02_*) into profiles/ under their judged names
+"""Copies the outputs of tools/gpu_final.sh (gpurun_out/f_* and gpurun_out/r02_*) into profiles/ under their judged names
 and prints the headline numbers (to be quoted in DESIGN.md / profiles/README.md)."""
 import json
 import os
@@ -14,7 +14,8 @@ MAP = {"f_bench.json": "r02_bench_n1.json", "f_bench_ref.json": "r02_bench_refer
        "f_pytest.log": "r02_pytest_gpu.log"}
 R02 = ["launches_unet_p64.csv", "launch_summary.txt", "dram_unet_p64.csv", "traffic.json", "spans_events.txt", "ncu_full_1.csv",
        "ncu_full_2.csv", "ncu_full_3.csv", "ncu_full_4.csv", "dwt_dram.csv", "bench_dwt.txt", "hfrm_launches.csv",
-       "hfrm_launch_summary.txt", "bench_hfrm.txt", "sampler_timeline.txt", "latency_small.txt", "lib_sha16.txt", "smi.txt"]
+       "hfrm_launch_summary.txt", "bench_hfrm.txt", "sampler_timeline.txt", "latency_small.txt", "lib_sha16.txt", "src_sha16.txt",
+       "smi.txt", "p1_spans_splitk.txt", "latency_small_nosplit.txt", "train_step.json", "train_step.txt"]
 
 
 def last_json(path):
