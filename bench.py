@@ -26,11 +26,15 @@ broadcast and the gather of restored images to rank 0 (inside the timed region).
 
   --config 5   : BASELINE.json configs[4] (512x512, grid_r = 16 -> 25 overlapping patches per image, 100 DDIM steps,
                  32 images per GPU); lines kept under profiles/
-  --precision fp32 : the parity-mode engine (3xTF32 tensor-core contractions / FFMA)
+  --precision fp32 : the parity-mode engine (tensor-core contractions through a 3-way bf16 split); fp32_ffma: CUDA cores
 
-The HFRM (one-shot high-frequency CNN, SURVEY.md 8f-1 "next") is bypassed in BOTH arms: the 45 high-frequency
-channels fed to the UNet are the HF bands of the DWT of the synthetic ground truth (the reference's own
-`if 0:` branch, restoration.py:99-100), so the two arms time the same computation.
+  single_image : (N = 1, default config) BASELINE.json configs[0]'s operating point on the GPU: batch 1, one latent patch per
+                 DDIM step, ms per step of the sampling loop (split-K contractions, graph replay); reported beside the metric
+
+The HFRM (one-shot high-frequency CNN) runs in BOTH arms (csrc/wdm_hfrm.cu here, oracle/hfrm_oracle.py in the
+CPU arms): `value` / `e2e` time the whole restore() computation. `--bypass-hfrm` restores the round-1 definition (the 45
+high-frequency channels fed to the UNet are the HF bands of the DWT of the synthetic ground truth, the reference's own
+`if 0:` branch, restoration.py:99-100).
 """
 import argparse
 import json
@@ -327,6 +331,31 @@ def parity_block(dev, precisions=("fp32", "fp32_ffma", "bf16"), batch=16, slots=
         del restorer
         torch.cuda.empty_cache()
     return res
+
+
+def single_image_latency(eng, betas, dev, steps=50):
+    """BASELINE.json configs[0]'s operating point on the GPU (batch 1, 256 x 256 = one 64 x 64 latent patch per DDIM step): the
+    sampling loop alone through DdimSampler (gather refresh -> UNet engine with split-K contractions -> DDIM update, replayed
+    as a CUDA graph), CUDA events around 3 runs of `steps` steps. Not the headline metric: reported beside it."""
+    from wavedm_b200.sampler import DdimSampler
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 3, 64, 64, generator=g).to(dev)
+    xc = torch.randn(1, 48, 64, 64, generator=g).to(dev)
+    xo = torch.randn(1, 45, 64, 64, generator=g).to(dev)
+    seq = list(range(0, 1000, 1000 // steps))
+    smp = DdimSampler(eng)
+    for _ in range(2):
+        smp.sample(x, xc, xo, seq, betas, [(0, 0)], 64, keep_history=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(3):
+        smp.sample(x, xc, xo, seq, betas, [(0, 0)], 64, keep_history=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    return {"ms_per_ddim_step": ms / steps, "ms_per_image_sampling": ms, "ddim_steps": steps, "patches_per_step": 1,
+            "what": "batch 1, 256x256: DdimSampler.sample alone (graph replay), bf16; HFRM / DWT / IWT not included"}
 
 
 def gpu_eager_baseline(dev, batch, ddim_sample_steps=3):
@@ -650,6 +679,9 @@ def main():
         cpu = parity = gpu_base = None
         # baselines and the parity block run at N = 1 only: at N > 1 the other ranks would spin in the closing barrier on the
         # host cores the CPU sample is timed on (and rank 0's GPU would idle through it in the driver's utilisation record)
+        single = None
+        if world == 1 and not args.wavelet_in_unet and args.config == 2 and args.precision == "bf16":
+            single = single_image_latency(eng, restorer.diffusion.betas, dev)
         if world == 1 and not args.wavelet_in_unet:
             del restorer, eng
             torch.cuda.empty_cache()
@@ -668,7 +700,7 @@ def main():
                        "d2h_bytes_per_step": int(B * 3 * H * W * 4) * world, "ms_per_step": ms_e2e,
                        "note": "every rank copies its own inputs H2D from pinned memory and its restored images D2H into pinned memory"},
                "gpu_launches": int(launches), "roofline": roof, "roofline_dwt": rdwt, "cpu_baseline": cpu,
-               "parity": parity, "gpu_eager_baseline": gpu_base, "hfrm": hfrm}
+               "parity": parity, "gpu_eager_baseline": gpu_base, "hfrm": hfrm, "single_image": single}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
