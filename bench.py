@@ -337,6 +337,7 @@ def single_image_latency(eng, betas, dev, steps=50):
     """BASELINE.json configs[0]'s operating point on the GPU (batch 1, 256 x 256 = one 64 x 64 latent patch per DDIM step): the
     sampling loop alone through DdimSampler (gather refresh -> UNet engine with split-K contractions -> DDIM update, replayed
     as a CUDA graph), CUDA events around 3 runs of `steps` steps. Not the headline metric: reported beside it."""
+    import torch
     from wavedm_b200.sampler import DdimSampler
     g = torch.Generator().manual_seed(1)
     x = torch.randn(1, 3, 64, 64, generator=g).to(dev)
