@@ -5,6 +5,8 @@ Tolerance: the kernel reproduces the rounding points of torch's CUDA foreach pat
 (fused multiply-add or not inside lerp / addcmul / addcdiv), which moves single results by one ulp: against the ORACLE
 parameters are compared to 2e-7 x max|p| + the size of one step's rounding (lr x 1e-5), moments to 1e-6 relative; against
 torch.optim.Adam on the same GPU the comparison is exact."""
+import os
+
 import pytest
 import torch
 
@@ -162,3 +164,107 @@ def test_denoising_diffusion_constructs_the_fused_update_on_cuda():
     assert isinstance(opt, optimize.FusedAdam) and opt.defaults["lr"] == 4e-5 and opt.defaults["betas"] == (0.9, 0.999)
     cfg.optim.optimizer = "SGD"
     assert type(optimize.get_optimizer(cfg, lin.parameters())) is torch.optim.SGD
+
+
+def _train_setup(tmp_path):
+    """DenoisingDiffusion_Wavelet on a small UNet (16 x 16 latent patches) with a two-batch synthetic training loader."""
+    import argparse
+    from oracle import unet_oracle as O
+    from wavedm_b200 import harness, optimize
+    from wavedm_b200.ddm_wavelet import DenoisingDiffusion_Wavelet
+    cfg = O.default_config(data__image_size=16, data__patch_size=64, model__ch=128, model__ch_mult=[1, 2],
+                           model__num_res_blocks=1, model__attn_resolutions=[8])
+    cfg.device = DEV
+    cfg.model.engine_precision = "fp32"
+    cfg.data.data_dir = str(tmp_path)
+    cfg.training.n_epochs = 1
+    cfg.model.use_gt_in_train = getattr(cfg.model, "use_gt_in_train", False)
+    args = argparse.Namespace(resume="", local_rank=0, sampling_timesteps=5, grid_r=16, image_folder=str(tmp_path),
+                              hfrm_ckpt=harness.synth_hfrm_checkpoint(61), test_set="raindrop", seed=61)
+    torch.manual_seed(61)
+    d = DenoisingDiffusion_Wavelet(args, cfg)     # the constructor itself picks FusedAdam and attaches the EMA on CUDA
+    assert isinstance(d.optimizer, optimize.FusedAdam) and d.optimizer._ema is not None
+    harness.seeded_unet_weights(d, 61)
+    d.ema_helper.shadow = {}
+    d.ema_helper.register(d.model)
+    g = torch.Generator().manual_seed(9)
+    batches = [(torch.rand(1, 4, 6, 64, 64, generator=g), ["a"], torch.zeros(1)) for _ in range(3)]
+
+    class DS:
+        def get_loaders(self, *a, **k):
+            return batches, batches
+    return d, DS(), cfg
+
+
+def test_train_loop_runs_the_fused_update_bit_identically_to_the_reference_objects(tmp_path):
+    """DenoisingDiffusion_Wavelet.train (ddm_wavelet.py:200-292) for three steps on CUDA. Inside the loop a twin set of
+    parameters is stepped with the reference's own objects -- torch.optim.Adam (utils/optimize.py:7-8) and the per-tensor EMA
+    loop (ddm_wavelet.py:48-53) -- on the SAME gradients: parameters and EMA shadows must stay bit-identical, with ONE launch
+    of this library per step. (Two separate training runs cannot be compared: Adam's first steps are lr * sign(g), and cuDNN's
+    backward does not reproduce the sign of a 1e-12 gradient.) Then the inference engine must see the trained weights (version
+    counters moved by the raw-pointer update) and the step-1 checkpoint must load into torch.optim.Adam."""
+    from wavedm_b200 import _lib
+    lib = _lib.load()
+    d, ds, cfg = _train_setup(str(tmp_path))
+    os.makedirs(os.path.join(cfg.data.data_dir, "ckpts"), exist_ok=True)
+    named = [(n, p) for n, p in d._unet().named_parameters() if p.requires_grad]
+    w0 = {n: p.detach().clone() for n, p in named}
+    twins = [torch.nn.Parameter(p.detach().clone()) for _, p in named]
+    topt = torch.optim.Adam(twins, lr=cfg.optim.lr, weight_decay=cfg.optim.weight_decay, betas=(0.9, 0.999), amsgrad=False,
+                            eps=cfg.optim.eps)
+    mu = d.ema_helper.mu
+    tshadow = [p.detach().clone() for p in twins]
+    real_step, real_update, launches = d.optimizer.step, d.ema_helper.update, []
+
+    def step():
+        for t, (_, p) in zip(twins, named):
+            t.grad = p.grad.detach().clone()
+        topt.step()
+        for i, t in enumerate(twins):
+            tshadow[i] = (1. - mu) * t.data + mu * tshadow[i]
+        n0 = lib.wdm_launch_counter()
+        real_step()
+        launches.append(lib.wdm_launch_counter() - n0)
+
+    def update(module):
+        n0 = lib.wdm_launch_counter()
+        real_update(module)
+        launches[-1] += lib.wdm_launch_counter() - n0
+    d.optimizer.step, d.ema_helper.update = step, update
+    xg = torch.Generator().manual_seed(77)
+    x = torch.randn(2, 96, 16, 16, generator=xg).to(DEV)
+    t = torch.tensor([10.0, 500.0], device=DEV)
+    with torch.no_grad():
+        y_before = d._unet().eval()(x, t).clone()    # packs the engine with the untrained weights
+    torch.manual_seed(123)
+    d.train(ds)
+    assert launches == [1, 1, 1]
+    moved = 0.0
+    for (n, p), tw, sh in zip(named, twins, tshadow):
+        assert torch.equal(p.data, tw.data), n
+        assert torch.equal(d.ema_helper.shadow[n], sh), n
+        moved = max(moved, float((p.data - w0[n]).abs().max()))
+    assert moved > 1e-5                                            # lr 4e-5: every step moves a weight by about lr
+    st = d.optimizer.state[named[0][1]]
+    assert float(st["step"]) == 3.0 and float(st["exp_avg"].abs().max()) > 0
+    # the packed inference engine follows the raw-pointer update
+    net = d._unet().eval()
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False   # strict fp32 comparator
+    try:
+        with torch.no_grad():
+            n0 = lib.wdm_launch_counter()
+            y_eng = net(x, t)
+            assert lib.wdm_launch_counter() > n0
+            y_ref = net._forward_autograd(x, t)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    err = float((y_eng - y_ref).abs().max())
+    assert err <= 5e-5 * float(y_ref.abs().max()), err
+    assert float((y_eng - y_before).abs().max()) > 20 * err          # ... and not the weights the engine was packed with before
+    # checkpoint written at step 1 (ddm_wavelet.py:277-286) loads into the reference's optimizer class
+    ck = torch.load(os.path.join(str(tmp_path), "ckpts", cfg.data.dataset + "_epoch1_ddpm.pth.tar"), map_location=DEV,
+                    weights_only=False)
+    lopt = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for _, p in named], lr=4e-5)
+    lopt.load_state_dict(ck["optimizer"])
+    assert float(lopt.state[lopt.param_groups[0]["params"][0]]["step"]) == 1.0

@@ -330,8 +330,9 @@ class DenoisingDiffusion_Wavelet(object):
 
     # ------------------------------------------------------------------------------------------ training
     def train(self, DATASET):
-        """ddm_wavelet.py:200-292: the reference's training step over the same parameters (PyTorch autograd;
-        DWT through the CUDA kernel). Not accelerated this round."""
+        """ddm_wavelet.py:200-292: the reference's training step over the same parameters. On CUDA the DWT, the HFRM call and
+        the parameter update (Adam + EMA shadow: one launch, csrc/wdm_optim.cu) run on this library's kernels; the UNet
+        forward / backward is PyTorch autograd."""
         cfg, cfgm = self.config, self.config.model
         train_loader, _ = DATASET.get_loaders()
         num_of_pixel = cfgm.pred_channels * cfg.data.image_size ** 2
