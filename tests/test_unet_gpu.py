@@ -191,6 +191,7 @@ SPLITK_CASES = [
     (1, 1024, 0, 512, 16, 3, 1, 0, 0, True, 2),        # smallest factor
     (1, 768, 0, 768, 8, 3, 1, 0, 0, False, 5),         # 108 k-blocks over 5 splits: uneven ranges
     (1, 512, 0, 256, 16, 3, 2, 0, 0, False, "plan"),   # stride-2 (out 8x8), M = 64
+    (16, 768, 0, 768, 8, 3, 1, 0, 16, True, "plan"),   # 16 patches at 8x8: 96 64-wide tiles are too many -> 128-wide tiles, S = 3
 ]
 
 

@@ -1411,7 +1411,7 @@ bool gemm_tc_supported(const GemmParams& p) {
     return true;
 }
 
-static int launch_gemm_tc_impl(const GemmParams& p, int ksplit, cudaStream_t s) {
+static int launch_gemm_tc_impl(const GemmParams& p, int ksplit, int ksplit_bn, cudaStream_t s) {
     if (!gemm_tc_supported(p)) return WDM_ERR_UNSUPPORTED;
     {
         static const int forced = []() {
@@ -1439,7 +1439,7 @@ static int launch_gemm_tc_impl(const GemmParams& p, int ksplit, cudaStream_t s) 
     if (small_bn && BN > 64 && !subpix && !p.b_batch_stride && !p.a_shared && !p.fuse_softmax && !p.a_split3 &&
         (long long)((p.M + kBM - 1) / kBM) * (p.N / BN) * 8 <= num_sms_tc())
         BN = 64;
-    if (ksplit > 1) BN = 64;  // split-K: 1-CTA tiles, as many weight streams as possible (gemm_tc_ksplit_plan checked the shape)
+    if (ksplit > 1) BN = ksplit_bn;  // split-K: 1-CTA tiles, as many weight streams as possible (ksplit_plan chose the width)
     static const int pair_enabled = []() {
         const char* e = getenv("WDM_TC_PAIR");
         return e ? atoi(e) : 1;
@@ -1689,7 +1689,7 @@ static int launch_gemm_tc_impl(const GemmParams& p, int ksplit, cudaStream_t s) 
 // k-blocks [s*kb/S, (s+1)*kb/S) and stores its raw fp32 accumulator to slab s of a scratch tensor (L2-resident: <= 10 MB);
 // splitk_finish_kernel adds the slabs in split order (deterministic) and applies the epilogue of epi_rows -- alpha, bias +
 // timestep row, residual, bf16 rounding, GroupNorm side-car with the same summation tree.
-int gemm_tc_ksplit_plan(const GemmParams& p) {
+static int ksplit_plan(const GemmParams& p, int* bn) {
     static const int enabled = []() {
         const char* e = getenv("WDM_TC_SPLITK");
         return e ? atoi(e) : 1;
@@ -1702,13 +1702,21 @@ int gemm_tc_ksplit_plan(const GemmParams& p) {
     if (p.temb && p.temb_rows > 1 && ((p.Hout * p.Wout) % 32)) return 1;
     const int kf = 1;
     const int kblocks = p.tail_1x1 ? p.K / kBK : p.taps * kf * (p.C0 + p.C1) / kBK;
-    const long long tiles = (long long)((p.M + kBM - 1) / kBM) * (p.N / 64);
-    if (tiles * 2 > num_sms_tc() || kblocks < 32) return 1;   // enough CTAs already, or nothing to split
+    if (kblocks < 32) return 1;                               // nothing to split
+    // 64-wide tiles give the most weight streams; 128-wide ones (half the A-tile re-reads) when those would be too many
+    const long long mt = (p.M + kBM - 1) / kBM;
+    int BN = 64;
+    long long tiles = mt * (p.N / 64);
+    if (tiles * 2 > num_sms_tc() && (p.N % 128) == 0) BN = 128, tiles = mt * (p.N / 128);
+    if (tiles * 2 > num_sms_tc()) return 1;                   // enough CTAs already
     long long S = num_sms_tc() / tiles;
     if (S > kblocks / 8) S = kblocks / 8;
     if (S > 32) S = 32;
+    if (bn) *bn = BN;
     return S >= 2 ? (int)S : 1;
 }
+
+int gemm_tc_ksplit_plan(const GemmParams& p) { return ksplit_plan(p, nullptr); }
 
 // One CTA per (32-row group, 32-column chunk); thread = (row, 4-column block): every slab load is a fully used 128-byte line
 // per 8 lanes and all S loads of a thread are independent (the first version had a thread walk a whole row chunk of every
@@ -1780,14 +1788,15 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 }
 
 int launch_gemm_tc(const GemmParams& p, cudaStream_t s) {
-    if (p.ksplit <= 1) return launch_gemm_tc_impl(p, 1, s);
-    if (!p.ksplit_scratch || p.ksplit > gemm_tc_ksplit_plan(p) || !wdm_aligned(p.ksplit_scratch, 16)) return WDM_ERR_BAD_ARG;
+    if (p.ksplit <= 1) return launch_gemm_tc_impl(p, 1, 0, s);
+    int bn = 64;
+    if (!p.ksplit_scratch || p.ksplit > ksplit_plan(p, &bn) || !wdm_aligned(p.ksplit_scratch, 16)) return WDM_ERR_BAD_ARG;
     GemmParams q = p;
     q.out = p.ksplit_scratch, q.out_dtype = DT_F32, q.ldo = p.N;
     q.alpha = 1.f, q.bias = nullptr, q.temb = nullptr, q.temb_rows = 0, q.residual = nullptr, q.stats_out = nullptr;
     q.ksplit = 0, q.ksplit_scratch = nullptr;
     if (!gemm_tc_supported(q)) return WDM_ERR_BAD_ARG;
-    int st = launch_gemm_tc_impl(q, p.ksplit, s);
+    int st = launch_gemm_tc_impl(q, p.ksplit, bn, s);
     if (st != WDM_OK) return st;
     dim3 grid((unsigned)((p.M + 31) / 32), (unsigned)(p.N / 32));
     cudaError_t e = wdm_launch_pdl(splitk_finish_kernel, grid, dim3(256), (size_t)0, s,
