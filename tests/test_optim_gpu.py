@@ -62,6 +62,15 @@ def test_fused_adam_vs_oracle_and_torch_cuda(wd):
             assert float((sa[k] - sb[k]).abs().max()) <= 1e-6 * float(o.abs().max()), (i, k)
     print(f"fused Adam vs torch.optim.Adam on the GPU after 6 steps (wd = {wd}): bit-identical = {exact}")
     assert exact   # same rounding points as torch's CUDA foreach kernels (csrc/wdm_optim.cu header)
+    # a parameter whose storage is replaced between steps (module.to(...), param.data = ...) is picked up: no stale pointers
+    ours[2].data = ours[2].data.clone()
+    grads = _grads(g, host, 3)
+    for a, b, gr in zip(ours, theirs, grads):
+        a.grad, b.grad = gr.to(DEV), gr.to(DEV)
+    opt.step()
+    ref.step()
+    for a, b in zip(ours, theirs):
+        assert torch.equal(a.data, b.data)
 
 
 def test_ema_update_kernel_is_bit_identical_to_the_reference_loop():

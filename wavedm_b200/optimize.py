@@ -122,7 +122,7 @@ class FusedAdam(optim.Adam):
                    sh.data_ptr() if fuse else 0, p.numel()) for p, sh in zip(plist, shadows or plist)]
         dev = plist[0].device if plist else None
         return {"has_grad": has_grad, "plist": plist, "step_buf": step_buf, "fuse": fuse, "shadows": shadows, "static": static,
-                "grad_ptrs": None, "grads": None,
+                "grad_ptrs": None, "grads": None, "param_ptrs": [p.data_ptr() for p in plist],
                 "buckets": [{"count": c, "idx": idx, "table": SegmentTable(dev)} for c, idx in sorted(buckets.items())]}
 
     @torch.no_grad()
@@ -141,8 +141,11 @@ class FusedAdam(optim.Adam):
             has_grad = [g is not None for g in grads_all]
             plan = self._plans.get(gi)
             if plan is None or plan["has_grad"] != has_grad or \
+                    [p.data_ptr() for p in plan["plist"]] != plan["param_ptrs"] or \
                     (plan["fuse"] and any(self._ema[0].shadow[self._ema[1][p]] is not sh
                                           for p, sh in zip(plan["plist"], plan["shadows"]))):
+                # first step, another set of parameters received gradients, a parameter's storage was replaced
+                # (module.to(...), param.data = ...), or the EMA helper holds new shadow tensors (load_state_dict)
                 plan = self._plans[gi] = self._build_plan(gi, group, has_grad)
             if not plan["plist"]:
                 continue
