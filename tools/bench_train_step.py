@@ -87,7 +87,9 @@ def main():
                 step_ms += ev[0].elapsed_time(ev[2])
         upd_ms /= a.steps
         step_ms /= a.steps
-        r = {"update_ms": round(upd_ms, 4), "step_ms": round(step_ms, 3), "params": n_params, "loss": float(loss),
+        if arm == "fused":
+            r_tab = sum(b["table"].uploads for pl in opt._plans.values() for b in pl["buckets"])
+        r = {"update_ms": round(upd_ms, 4), "step_ms": round(step_ms, 3), "params": n_params, "loss": float(loss.detach()),
              "kernel_launches_of_this_library_in_update": int(launches)}
         if arm == "fused":
             # the launch alone: back-to-back updates on the last gradients (GPU-bound: the host side is ~0.4 ms per call)
@@ -99,6 +101,7 @@ def main():
             torch.cuda.synchronize()
             k_ms = ev[0].elapsed_time(ev[1]) / 10
             r["kernel_ms"] = round(k_ms, 4)
+            r["pointer_table_uploads"] = int(r_tab)   # 1 = the gradient tensors kept their addresses over all steps
             upd_ms_in_step, upd_ms = upd_ms, k_ms
             alg = 36.0 * n_params
             peak = float(peaks.get("hbm_gbs", 0) or 0)

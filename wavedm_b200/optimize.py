@@ -18,6 +18,7 @@ class SegmentTable:
         self.rows: Optional[List[Tuple[int, ...]]] = None
         self.segs = self.first = None
         self.n_ctas = 0
+        self.uploads = 0
 
     def update(self, rows: List[Tuple[int, ...]]):
         if rows != self.rows:
@@ -27,6 +28,25 @@ class SegmentTable:
             self.segs = torch.tensor(rows, dtype=torch.int64).reshape(-1, 6).to(self.device)
             self.first = torch.tensor(first, dtype=torch.int32).to(self.device)
             self.rows, self.n_ctas = rows, first[-1]
+            self.uploads += 1
+        return self
+
+    def set_column(self, col: int, values: List[int]):
+        """Replaces one column of the table (the gradient pointers: autograd hands out new gradient tensors every step after
+        zero_grad(set_to_none=True)): one list -> tensor conversion and one 5.6 KB asynchronous copy from pinned memory."""
+        if self.rows is None or len(values) != len(self.rows):
+            raise ValueError("SegmentTable.set_column: table not built / wrong length")
+        if getattr(self, "_pin", None) is None or self._pin.shape[0] != len(values):
+            self._pin = torch.empty(len(values), dtype=torch.int64).pin_memory()
+            self._ev = None
+        if self._ev is not None:
+            self._ev.synchronize()   # the previous copy out of the pinned buffer has been issued long ago; never waits in practice
+        self._pin.copy_(torch.tensor(values, dtype=torch.int64))
+        with torch.cuda.device(self.device):
+            self.segs[:, col].copy_(self._pin, non_blocking=True)
+            self._ev = torch.cuda.Event()
+            self._ev.record()
+        self.uploads += 1   # self.rows keeps the column it was built with: callers of set_column track that column themselves
         return self
 
     def launch(self, do_adam, do_ema, lr=0.0, beta1=0.0, beta2=0.0, eps=0.0, weight_decay=0.0, step=1, mu=0.0):
@@ -122,7 +142,7 @@ class FusedAdam(optim.Adam):
                    sh.data_ptr() if fuse else 0, p.numel()) for p, sh in zip(plist, shadows or plist)]
         dev = plist[0].device if plist else None
         return {"has_grad": has_grad, "plist": plist, "step_buf": step_buf, "fuse": fuse, "shadows": shadows, "static": static,
-                "grad_ptrs": None, "grads": None, "param_ptrs": [p.data_ptr() for p in plist],
+                "grad_ptrs": None, "param_ptrs": [p.data_ptr() for p in plist],
                 "buckets": [{"count": c, "idx": idx, "table": SegmentTable(dev)} for c, idx in sorted(buckets.items())]}
 
     @torch.no_grad()
@@ -158,10 +178,15 @@ class FusedAdam(optim.Adam):
                         raise RuntimeError("FusedAdam: gradient does not match its parameter")
                 st_ = plan["static"]
                 for b in plan["buckets"]:
-                    b["table"].update([(st_[i][0], ptrs[i], st_[i][1], st_[i][2], st_[i][3], st_[i][4]) for i in b["idx"]
-                                       if st_[i][4]])
+                    live = [i for i in b["idx"] if st_[i][4]]
+                    if b["table"].rows is None:
+                        b["table"].update([(st_[i][0], ptrs[i], st_[i][1], st_[i][2], st_[i][3], st_[i][4]) for i in live])
+                    else:
+                        b["table"].set_column(1, [ptrs[i] for i in live])
                 plan["grad_ptrs"] = ptrs
-            plan["grads"] = grads   # keeps the tensors behind the tables' pointers alive until the next step
+            # no reference to the gradient tensors is kept: the launch is stream-ordered, and a held reference would make
+            # zero_grad(set_to_none=True) + backward allocate NEW gradients every step (other pointers -> table rebuilt
+            # and re-uploaded every step, and twice the gradient memory)
             plan["step_buf"] += 1
             beta1, beta2 = group["betas"]
             for b in plan["buckets"]:
