@@ -489,6 +489,34 @@ def test_unet_full_bf16_tc_vs_reference_golden():
     assert tc_n >= 70 and tc_fl > 0.95 * (tc_fl + s_fl), (tc_n, s_n, tc_fl, s_fl)
 
 
+def test_unet_full_bf16_single_patch_runs_splitk_and_matches_the_batched_call():
+    """The single-image operating point (BASELINE configs[0]: one latent patch per DDIM step): the engine splits the deep-K
+    contractions over idle SMs (reduce launches on top of the 181 of a batched call) and patch 0 of the reference golden comes
+    out the same as in the two-patch call (same parity gate)."""
+    from wavedm_b200 import _lib
+    g = golden("unet_full.npz")
+    cfg = O.default_config()
+    sd = O.init_state_dict(cfg, seed=int(g["seed"]))
+    eng = _engine(cfg, sd, "bf16")
+    gen = torch.Generator().manual_seed(int(g["x_seed"]))
+    x = torch.randn(2, 96, 64, 64, generator=gen)
+    t = torch.from_numpy(g["t"])
+    lib = _lib.load()
+    eng.forward(x[:1].to(DEV), t.to(DEV))
+    n0 = lib.wdm_launch_counter()
+    out1 = eng.forward(x[:1].to(DEV), t.to(DEV)).cpu()
+    n1 = lib.wdm_launch_counter() - n0
+    n0 = lib.wdm_launch_counter()
+    out64 = eng.forward(x.repeat(32, 1, 1, 1).to(DEV), t.to(DEV)).cpu()     # one timestep for all patches (the sampler's case)
+    n64 = lib.wdm_launch_counter() - n0
+    assert n1 >= n64 + 20, (n1, n64)          # split-K: one reduce / epilogue launch per split contraction
+    ref = torch.from_numpy(g["out"])[:1]
+    rel = ((out1 - ref).norm() / ref.norm()).item()
+    assert rel <= 3e-2, rel
+    rel64 = ((out64[:1] - ref).norm() / ref.norm()).item()
+    assert rel64 <= 3e-2 and abs(rel - rel64) <= 5e-3, (rel, rel64)
+
+
 def test_unet_full_fp32_vs_reference_golden():
     g = golden("unet_full.npz")
     cfg = O.default_config()
